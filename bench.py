@@ -1,0 +1,254 @@
+#!/usr/bin/env python
+"""bench.py -- KRN 224x224 training throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 30 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's algorithm on the host CPU (oracle port)
+
+Workload = BASELINE.json configs[1]: KRN train, bs=48/GPU, AdamW (lr 1e-3, betas .9/.999, wd .01),
+clip_grad_norm 1.0, 224x224 synthetic images in [0,1), random-init weights (no network for ImageNet).
+One "step" = zero grads, forward, loss, backward, [grad allreduce], clip, AdamW on one batch.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 48
+HW = 224
+METRIC = 'krn_train_images_per_sec'
+UNIT = 'images/s'
+
+
+def _peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get('hbm_gbs', 6650.0), d.get('bf16_tflops_sustained', 1400.0), 'measured'
+    return 6650.0, 1590.0, 'fallback'
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._halt = index, [], threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(',')]
+                if len(f) >= 7:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=6)
+        sm = sorted(int(float(r[0])) for r in self.rows if r[0].replace('.', '').isdigit())
+        mx = [int(float(r[1])) for r in self.rows if r[1].replace('.', '').isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's algorithm on the host cores: oracle port (oracle/steps.py), all threads."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import torch
+    from oracle import krn as okrn, synth, steps
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synth.synth_state_dict(okrn.krn_shapes(), 2021)
+    st = steps.new_state(sd)
+    x, y = synth.synth_images(BATCH), synth.synth_keypoints(BATCH)
+    for _ in range(max(1, min(args.warmup, 2))):
+        steps.krn_train_step(sd, st, x, y)
+    k = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(k):
+        steps.krn_train_step(sd, st, x, y)
+    dt = (time.perf_counter() - t0) / k
+    v = BATCH / dt
+    sample = '%d full bs=%d train steps of the oracle port (torch CPU ops, %d threads)' % (k, BATCH, cores)
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': k,
+        'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
+        'config': {'workload': 'KRN train bs=48 AdamW 224x224 synthetic (BASELINE.json configs[1])', 'device': 'host CPU'},
+        'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+
+
+def cpu_baseline(steps_n=3):
+    import torch
+    from oracle import krn as okrn, synth, steps
+    cores = os.cpu_count() or 1
+    nt = torch.get_num_threads()
+    torch.set_num_threads(cores)
+    sd = synth.synth_state_dict(okrn.krn_shapes(), 2021)
+    st = steps.new_state(sd)
+    x, y = synth.synth_images(BATCH), synth.synth_keypoints(BATCH)
+    steps.krn_train_step(sd, st, x, y)
+    t0 = time.perf_counter()
+    for _ in range(steps_n):
+        steps.krn_train_step(sd, st, x, y)
+    dt = (time.perf_counter() - t0) / steps_n
+    torch.set_num_threads(nt)
+    return {'value': BATCH / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': '%d full bs=%d KRN train steps of the oracle port (torch CPU, %d threads), %.2f s/step' % (steps_n, BATCH, cores, dt)}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200')
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile-out', default='')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from speedplusbaseline_b200 import _lib as L
+    from speedplusbaseline_b200 import profiler
+    from speedplusbaseline_b200.nets.park2019 import KeypointRegressionNet
+    from speedplusbaseline_b200.optim import FusedAdamW
+    from speedplusbaseline_b200.core.trainer import KRNTrainStep
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+
+    model = KeypointRegressionNet(11, device=dev, seed=2021)
+    model.train()
+    opt = FusedAdamW(model._store, model.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
+                     clip_mode=1, max_norm=1.0)
+    if world > 1:
+        opt.grad_scale = 1.0 / world
+    stepper = KRNTrainStep(model, opt, use_graph=not args.no_graph, world_size=world)
+    g = torch.Generator(device='cpu').manual_seed(2021 + rank)
+    h_img = torch.rand(BATCH, 3, HW, HW, generator=g).pin_memory()
+    h_tgt = torch.rand(BATCH, 2, 11, generator=g).pin_memory()
+    d_img, d_tgt = h_img.to(dev), h_tgt.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # launches per step (counted on an eager step; graph replays re-issue the same kernels)
+    n0 = L.lib.b200sp_launch_count()
+    stepper.eager(d_img, d_tgt)
+    torch.cuda.synchronize()
+    launches_per_step = int(L.lib.b200sp_launch_count() - n0)
+
+    for _ in range(W):
+        stepper.step(d_img, d_tgt)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    # ---- timed region 1: device-resident inputs (kernel/graph throughput) -----------------------
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        loss3 = stepper.step(d_img, d_tgt)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    # ---- timed region 2: end to end through the public step API with HOST inputs ------------------
+    host_loss = torch.empty(3).pin_memory()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    last = None
+    for _ in range(K):
+        di = h_img.to(dev, non_blocking=True)
+        dt_ = h_tgt.to(dev, non_blocking=True)
+        l3 = stepper.step(di, dt_)
+        host_loss.copy_(l3, non_blocking=True)
+        last = float(host_loss[0])          # previous step's value unless the copy already landed
+    e3.record()
+    barrier()
+    final_loss = float(host_loss[0])
+    ms_e2e = e2.elapsed_time(e3)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        hbm, tf, which = _peaks()
+        value = world * BATCH * K / (ms / 1e3)
+        e2e = world * BATCH * K / (ms_e2e / 1e3)
+        prof = profiler.profile_krn_step(stepper, d_img, d_tgt, reps=3)
+        dom = prof['dominant']
+        roof = {'bound': 'hbm', 'kernel': dom['name'], 'achieved': dom['gbs'], 'peak': hbm, 'unit': 'GB/s',
+                'frac': dom['gbs'] / hbm, 'traffic': None, 'peak_source': which + ' (sustained copy)',
+                'share_of_step': dom['share'], 'us_per_launch': dom['us'], 'algorithmic_bytes_per_launch': dom['bytes'],
+                'step_roofline_frac': prof['step_roofline_ms'] / (ms / K),
+                'step_algorithmic_gb': prof['step_bytes'] / 1e9}
+        if args.profile_out:
+            with open(args.profile_out, 'w') as f:
+                f.write(prof['table'])
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
+            'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'fp32', 'data': 'synthetic',
+            'config': {'workload': 'KRN train bs=48/GPU AdamW 224x224 synthetic (BASELINE.json configs[1])',
+                       'math': 'fp32 storage, 3xTF32 tensor-core GEMMs + fp32 CUDA-core stencils',
+                       'global_batch': world * BATCH, 'parallelism': 'dp%d' % world,
+                       'cuda_graph': not args.no_graph,
+                       'l2': 'per-step working set ~2.7 GB of activations >> 126 MB L2 (no explicit flush)'},
+            'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(h_img.numel() * 4 + h_tgt.numel() * 4),
+                    'd2h_bytes_per_step': 12, 'ms_per_step': ms_e2e / K},
+            'gpu_launches': launches_per_step * K, 'launches_per_step': launches_per_step,
+            'clocks': clocks, 'roofline': roof, 'final_loss': final_loss,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line['cpu_baseline'] = cpu_baseline()
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

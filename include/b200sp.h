@@ -1,0 +1,186 @@
+/*
+ * b200sp.h -- C-ABI of libb200sp.so: the sm_100a kernels behind the
+ * speedplusbaseline CNN-training hot path (KRN / SPN / style-aug / DANN / AdamW).
+ *
+ * The reference (pure Python) has no FFI of its own: every entry point below
+ * replaces one torch op *call site* of the reference, cited per function as
+ * /root/reference/<file>:<line>.  The binding a maintainer adds is a ctypes
+ * stub; speedplusbaseline_b200/_lib.py is that stub.
+ *
+ * Conventions
+ *  - all pointers are DEVICE pointers unless the name ends in _host;
+ *  - activations are NHWC, contiguous, element type selected by `dtype`
+ *    (B200SP_F32 = float, B200SP_BF16 = __nv_bfloat16); parameters, BatchNorm
+ *    statistics and optimizer state are always float;
+ *  - every launcher enqueues on `stream` (a cudaStream_t passed as void*),
+ *    never synchronises, never allocates, and returns 0 or a cudaError_t /
+ *    negative B200SP_E* code;
+ *  - a "virtual tensor" (b200sp_vtensor) is a raw conv output plus the
+ *    per-channel affine + activation that the reference would have
+ *    materialised with batch_norm/relu6 -- consumers apply it on load, so the
+ *    normalised tensor never round-trips through HBM.
+ */
+#ifndef B200SP_H
+#define B200SP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SP_F32 0
+#define B200SP_BF16 1
+
+#define B200SP_ACT_NONE 0
+#define B200SP_ACT_RELU 1
+#define B200SP_ACT_RELU6 2
+#define B200SP_ACT_LEAKY02 3   /* LeakyReLU(0.2), park2019.py:66 */
+#define B200SP_ACT_SIGMOID 4   /* forward only, ghiasi.py:135 */
+
+#define B200SP_VT_PLAIN 0      /* v = x                                   */
+#define B200SP_VT_BNACT 1      /* v = act(x * p0[c] + p1[c])              */
+#define B200SP_VT_DY 2         /* v = p0[c]*x + p1[c]*x2 + p2[c]  (BN backward folded into the load) */
+
+#define B200SP_EINVAL (-22)
+#define B200SP_ENOSYS (-38)
+
+typedef struct b200sp_vtensor {
+    const void *x;      /* raw tensor */
+    const void *x2;     /* second tensor for B200SP_VT_DY (the saved raw conv output), else NULL */
+    const float *p0;    /* per-channel parameters, see modes above */
+    const float *p1;
+    const float *p2;
+    int32_t mode;
+    int32_t act;
+} b200sp_vtensor;
+
+/* Training-mode BatchNorm statistics fused into the producing conv's epilogue
+ * (replaces the stats half of torch batch_norm at park2019.py:48,52,64 and
+ * torchvision mobilenetv2.py:38,52).  The last CTA to finish turns the
+ * per-channel sums into scale/shift (+ saved mean/rstd), updates the running
+ * statistics (momentum, unbiased variance) and re-zeroes sum/sumsq/ticket. */
+typedef struct b200sp_bnfwd {
+    double *sum;              /* [C] zero on entry, zero on exit */
+    double *sumsq;            /* [C] */
+    uint32_t *ticket;         /* [1] zero on entry, zero on exit */
+    const float *gamma;       /* [C] */
+    const float *beta;        /* [C] */
+    float *running_mean;      /* [C] updated in place (may be NULL) */
+    float *running_var;       /* [C] */
+    float *scale;             /* [C] out: gamma * rstd */
+    float *shift;             /* [C] out: beta - mean * scale */
+    float *mean;              /* [C] out */
+    float *rstd;              /* [C] out */
+    float momentum;
+    float eps;
+} b200sp_bnfwd;
+
+/* BatchNorm backward reductions fused into the epilogue of the kernel that
+ * produces g = dL/d(act output) * act'(z):  s1 = sum g, s2 = sum g*xhat.
+ * The last CTA writes dgamma/dbeta (accumulating) and the coefficients of
+ * dy = cA*g + cB*y + cC, which the next consumer applies on load (VT_DY). */
+typedef struct b200sp_bnbwd {
+    double *s1;               /* [C] zero on entry/exit */
+    double *s2;               /* [C] */
+    uint32_t *ticket;
+    const void *y;            /* saved raw conv output of the BN input (same shape as g) */
+    const float *scale;       /* [C] forward-saved */
+    const float *shift;
+    const float *mean;
+    const float *rstd;
+    float *cA;                /* [C] out */
+    float *cB;
+    float *cC;
+    float *dgamma;            /* [C] += s2 */
+    float *dbeta;             /* [C] += s1 */
+    int32_t act;              /* activation that followed this BN */
+    int32_t pad_;
+} b200sp_bnbwd;
+
+/* ---- library ------------------------------------------------------------ */
+int b200sp_version(void);
+/* number of kernel launches issued through this library since load (the bench's gpu_launches) */
+int64_t b200sp_launch_count(void);
+
+/* ---- convolutions -------------------------------------------------------- */
+/* 3x3 stride-2 pad-1 stem, 3 -> Cout(32), NCHW float input (what the loader yields),
+ * NHWC output.  torchvision mobilenetv2.py:126 via park2019.py:107-108. */
+int b200sp_stem_fwd(const float *x_nchw, const float *w /*[32,3,3,3]*/, void *y,
+                    const b200sp_bnfwd *bn /*NULL in eval*/, int B, int H, int W, int dtype, void *stream);
+int b200sp_stem_wgrad(const float *x_nchw, const b200sp_vtensor *dy, float *dw /*[32,27] +=*/,
+                      int B, int H, int W, int dtype, void *stream);
+
+/* 1x1 convolution as GEMM  Y[M,N] = f(X)[M,K] * W[N,K]^T   (park2019.py:51,64;
+ * torchvision mobilenetv2.py:38,52).  bias may be NULL; out_act applied after bias
+ * (domain head revgrad.py:76-77, SPN FC spn.py:80-99). */
+int b200sp_pw_fwd(const b200sp_vtensor *x, const float *w, const float *bias, int out_act, void *y,
+                  const b200sp_bnfwd *bn /*may be NULL*/, int M, int N, int K, int dtype, void *stream);
+/* dX[M,K] = dY[M,N] * W[N,K] (+ skip);  then g = dX * act'(z) and the BN-backward
+ * reductions of the *input's* BatchNorm when `bn` is given.  scale_out multiplies the
+ * result first (gradient reversal: -alpha, revgrad.py:52-56). */
+int b200sp_pw_dgrad(const b200sp_vtensor *dy, const float *w, const void *skip, float scale_out,
+                    void *g, const b200sp_bnbwd *bn /*may be NULL*/, int M, int N, int K, int dtype, void *stream);
+/* dW[N,K] += dY[M,N]^T * f(X)[M,K];  dbias[N] += column sums of dY when dbias != NULL */
+int b200sp_pw_wgrad(const b200sp_vtensor *dy, const b200sp_vtensor *x, float *dw, float *dbias,
+                    int M, int N, int K, int dtype, void *stream);
+
+/* depthwise 3x3 pad 1, stride 1|2, weights [9][C] (tap-major).  park2019.py:47;
+ * torchvision mobilenetv2.py:45-49. */
+int b200sp_dw_fwd(const b200sp_vtensor *x, const float *w9c, void *y, const b200sp_bnfwd *bn,
+                  int B, int H, int W, int C, int stride, int dtype, void *stream);
+/* fused depthwise dgrad + wgrad + activation/BN backward of the conv INPUT:
+ *   g_in = (dgrad(dy) [+ skip]) * act'(z_in);  dw9c += wgrad;  BN reductions for the input's BN. */
+int b200sp_dw_bwd(const b200sp_vtensor *dy, const b200sp_vtensor *x, const float *w9c, const void *skip,
+                  void *g_in, float *dw9c, const b200sp_bnbwd *bn,
+                  int B, int H, int W, int C, int stride, int dtype, void *stream);
+
+/* ---- normalisation / elementwise ----------------------------------------- */
+/* out = y*scale + shift (+ residual), materialising a block output (mobilenetv2.py:61-62) */
+int b200sp_bn_apply(const void *y, const float *scale, const float *shift, const void *residual,
+                    int act, void *out, int64_t M, int C, int dtype, void *stream);
+/* eval mode: scale/shift from running statistics for `n` channels at once */
+int b200sp_bn_eval_affine(const float *gamma, const float *beta, const float *rmean, const float *rvar,
+                          float eps, float *scale, float *shift, int64_t n, void *stream);
+/* standalone versions of the fused "last CTA" steps */
+int b200sp_bn_fwd_finalize(const b200sp_bnfwd *bn, int C, double count, void *stream);
+int b200sp_bn_bwd_finalize(const b200sp_bnbwd *bn, int C, double count, void *stream);
+/* s1/s2 reductions for a materialised gradient (g, y) pair, then finalize */
+int b200sp_bn_bwd_reduce(const void *g, const b200sp_bnbwd *bn, int64_t M, int C, int dtype, void *stream);
+int b200sp_add_i64(int64_t *p, int64_t n, int64_t v, void *stream);     /* num_batches_tracked += 1 */
+
+/* RouterV2 space-to-depth + concat (park2019.py:70-80): out[B,h,w,4*Cr + C1] */
+int b200sp_reorg_cat_fwd(const b200sp_vtensor *xr /*[B,2h,2w,Cr]*/, const b200sp_vtensor *x1 /*[B,h,w,C1]*/,
+                         void *out, int B, int h, int w, int Cr, int C1, int dtype, void *stream);
+int b200sp_reorg_cat_bwd(const void *dcat, void *g_r, void *g_1, const b200sp_bnbwd *bn_r,
+                         const b200sp_bnbwd *bn_1, int B, int h, int w, int Cr, int C1, int dtype, void *stream);
+
+/* ---- KRN head + loss ------------------------------------------------------ */
+/* 7x7 valid conv 1024 -> 22 == FC over the NHWC-flattened map (park2019.py:121,139).
+ * logits[B,N] must hold the bias on entry (b200sp_krn_loss_prep); accumulates atomically. */
+int b200sp_head_fwd(const b200sp_vtensor *x, const float *w /*[N][HW*C]*/, float *logits,
+                    int B, int HWC, int C, int N, int dtype, void *stream);
+int b200sp_head_bias(const float *bias, float *logits, int B, int N, void *stream);
+/* park2019.py:142-160: loss3 = {loss, loss_x, loss_y}; dlogits = 2(x-t)/B * loss_scale[0] */
+int b200sp_krn_loss(const float *logits, const float *target /*[B,2,N/2]*/, float *loss3, float *dlogits,
+                    float *dbias /* += */, const float *loss_scale /*NULL => 1*/, int B, int N, void *stream);
+int b200sp_head_bwd(const float *dlogits, const b200sp_vtensor *x, const float *w, void *g, float *dw /* += */,
+                    float *dbias /* += */, const b200sp_bnbwd *bn, int B, int HWC, int C, int N, int dtype, void *stream);
+
+/* ---- optimizer (build.py:72-74 torch.optim.AdamW; trainer.py:97 clip_grad_norm_) ---- */
+typedef struct b200sp_adamw_hp {   /* lives in DEVICE memory so CUDA graphs can replay */
+    float lr, beta1, beta2, eps, weight_decay, max_norm, clip_value, grad_scale;
+    int32_t step;                  /* incremented by b200sp_adamw_step */
+    int32_t clip_mode;             /* 0 none, 1 global L2 norm (KRN/DANN), 2 value (SPN) */
+    double sqnorm;                 /* scratch: sum g^2 (zero on entry/exit) */
+    float last_norm;               /* out: total grad norm of the last step */
+    float pad_;
+} b200sp_adamw_hp;
+int b200sp_grad_sqnorm(const float *g, int64_t n, b200sp_adamw_hp *hp, void *stream);
+int b200sp_adamw_step(float *p, const float *g, float *m, float *v, void *p_lowp /*bf16 copy or NULL*/,
+                      int64_t n, b200sp_adamw_hp *hp, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SP_H */

@@ -1,0 +1,109 @@
+"""ctypes binding of libb200sp.so (include/b200sp.h).  This is the reference-side stub of
+INTEGRATION.md.  There is NO fallback: if the library is missing the import fails loudly."""
+import ctypes as C
+import os
+
+import torch
+
+from . import _build
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_RELU6, ACT_LEAKY02, ACT_SIGMOID = 0, 1, 2, 3, 4
+VT_PLAIN, VT_BNACT, VT_DY = 0, 1, 2
+
+vp = C.c_void_p
+
+
+class VTensor(C.Structure):
+    _fields_ = [('x', vp), ('x2', vp), ('p0', vp), ('p1', vp), ('p2', vp), ('mode', C.c_int32), ('act', C.c_int32)]
+
+
+class BnFwd(C.Structure):
+    _fields_ = [('sum', vp), ('sumsq', vp), ('ticket', vp), ('gamma', vp), ('beta', vp),
+                ('running_mean', vp), ('running_var', vp), ('scale', vp), ('shift', vp),
+                ('mean', vp), ('rstd', vp), ('momentum', C.c_float), ('eps', C.c_float)]
+
+
+class BnBwd(C.Structure):
+    _fields_ = [('s1', vp), ('s2', vp), ('ticket', vp), ('y', vp), ('scale', vp), ('shift', vp),
+                ('mean', vp), ('rstd', vp), ('cA', vp), ('cB', vp), ('cC', vp), ('dgamma', vp), ('dbeta', vp),
+                ('act', C.c_int32), ('pad_', C.c_int32)]
+
+
+class AdamWHp(C.Structure):
+    _fields_ = [('lr', C.c_float), ('beta1', C.c_float), ('beta2', C.c_float), ('eps', C.c_float),
+                ('weight_decay', C.c_float), ('max_norm', C.c_float), ('clip_value', C.c_float),
+                ('grad_scale', C.c_float), ('step', C.c_int32), ('clip_mode', C.c_int32),
+                ('sqnorm', C.c_double), ('last_norm', C.c_float), ('pad_', C.c_float)]
+
+
+def _load():
+    path = _build.LIB
+    if not os.path.exists(path):
+        if os.environ.get('B200SP_NO_AUTOBUILD'):
+            raise ImportError('libb200sp.so missing (%s); run `python -c "import __graft_entry__ as g; g.build()"`' % path)
+        _build.build()
+    return C.CDLL(path)
+
+
+lib = _load()
+i32, i64, f32, f64 = C.c_int, C.c_int64, C.c_float, C.c_double
+PVT, PBF, PBB = C.POINTER(VTensor), C.POINTER(BnFwd), C.POINTER(BnBwd)
+
+_SIGS = {
+    'b200sp_version': ([], i32),
+    'b200sp_launch_count': ([], i64),
+    'b200sp_stem_fwd': ([vp, vp, vp, PBF, i32, i32, i32, i32, vp], i32),
+    'b200sp_stem_wgrad': ([vp, PVT, vp, i32, i32, i32, i32, vp], i32),
+    'b200sp_pw_fwd': ([PVT, vp, vp, i32, vp, PBF, i32, i32, i32, i32, vp], i32),
+    'b200sp_pw_dgrad': ([PVT, vp, vp, f32, vp, PBB, i32, i32, i32, i32, vp], i32),
+    'b200sp_pw_wgrad': ([PVT, PVT, vp, vp, i32, i32, i32, i32, vp], i32),
+    'b200sp_dw_fwd': ([PVT, vp, vp, PBF, i32, i32, i32, i32, i32, i32, vp], i32),
+    'b200sp_dw_bwd': ([PVT, PVT, vp, vp, vp, vp, PBB, i32, i32, i32, i32, i32, i32, vp], i32),
+    'b200sp_bn_apply': ([vp, vp, vp, vp, i32, vp, i64, i32, i32, vp], i32),
+    'b200sp_bn_eval_affine': ([vp, vp, vp, vp, f32, vp, vp, i64, vp], i32),
+    'b200sp_bn_fwd_finalize': ([PBF, i32, f64, vp], i32),
+    'b200sp_bn_bwd_finalize': ([PBB, i32, f64, vp], i32),
+    'b200sp_bn_bwd_reduce': ([vp, PBB, i64, i32, i32, vp], i32),
+    'b200sp_add_i64': ([vp, i64, i64, vp], i32),
+    'b200sp_reorg_cat_fwd': ([PVT, PVT, vp, i32, i32, i32, i32, i32, i32, vp], i32),
+    'b200sp_reorg_cat_bwd': ([vp, vp, vp, PBB, PBB, i32, i32, i32, i32, i32, i32, vp], i32),
+    'b200sp_head_fwd': ([PVT, vp, vp, i32, i32, i32, i32, i32, vp], i32),
+    'b200sp_head_bias': ([vp, vp, i32, i32, vp], i32),
+    'b200sp_krn_loss': ([vp, vp, vp, vp, vp, vp, i32, i32, vp], i32),
+    'b200sp_head_bwd': ([vp, PVT, vp, vp, vp, vp, PBB, i32, i32, i32, i32, i32, vp], i32),
+    'b200sp_grad_sqnorm': ([vp, i64, vp, vp], i32),
+    'b200sp_adamw_step': ([vp, vp, vp, vp, vp, i64, vp, vp], i32),
+}
+for _n, (_a, _r) in _SIGS.items():
+    _f = getattr(lib, _n)
+    _f.argtypes, _f.restype = _a, _r
+
+EXPORTS = tuple(_SIGS)
+
+
+class B200SPError(RuntimeError):
+    pass
+
+
+def check(rc, what=''):
+    if rc != 0:
+        raise B200SPError('libb200sp %s failed with code %d' % (what, rc))
+
+
+def call(name, *args):
+    check(getattr(lib, name)(*args), name)
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise B200SPError('a CUDA device (B200, sm_100a) is required: there is no CPU fallback in '
+                          'speedplusbaseline_b200; use --no_cuda to run the unmodified torch path')

@@ -1,0 +1,136 @@
+"""Epoch loops with the reference's signatures (/root/reference/src/core/trainer.py:41-199) on top
+of a fused, CUDA-graph-captured training step.
+
+Reference step (trainer.py:64-98): H2D -> [style-aug] -> forward(+loss, 2 host syncs) -> zero_grad ->
+backward -> clip_grad_norm_(1.0) -> AdamW.  Here the whole device part is ONE graph launch:
+memset(grads) -> forward kernels -> backward kernels -> [NCCL allreduce] -> sqnorm -> AdamW;
+losses are read back asynchronously, so there is no per-iteration host sync.
+"""
+import logging
+import random
+import time
+
+import torch
+
+from .. import _lib as L
+from ..utils import AverageMeter, report_progress
+
+logger = logging.getLogger("Training")
+
+
+class KRNTrainStep:
+    """One fused KRN training iteration.  `step(images, target)` consumes device tensors
+    ([B,3,H,W] fp32 in [0,1], [B,2,K] fp32) and returns the device tensor loss3 = (loss, loss_x, loss_y)."""
+
+    def __init__(self, model, optimizer, use_graph=True, world_size=1, process_group=None):
+        self.model, self.opt, self.use_graph = model, optimizer, use_graph
+        self.world, self.pg = world_size, process_group
+        self._graphs = None
+        self._static = None
+        self._sig = None
+
+    # the un-captured sequence (also used for warm-up and as the eager fallback for odd batch sizes)
+    def _fwd_bwd(self, images, target):
+        eng = self.model.engine
+        eng.store.grads.zero_()
+        cx = eng.forward(images, target, train=True)
+        eng.backward(cx)
+        return cx
+
+    def _update(self):
+        self.opt.step(sync=False)
+
+    def _allreduce(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.model.engine.store.grads, group=self.pg)
+
+    def eager(self, images, target):
+        self.opt.sync_hyperparams()
+        cx = self._fwd_bwd(images, target)
+        self._allreduce()
+        self._update()
+        return cx.loss3
+
+    def _capture(self, images, target):
+        self._static = (torch.empty_like(images), torch.empty_like(target))
+        self._static[0].copy_(images)
+        self._static[1].copy_(target)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):          # warm-up allocates every activation buffer
+            cx = self._fwd_bwd(*self._static)
+            # undo the warm-up's side effects on BN running statistics / counters? No: a warm-up
+            # step is a real step for BN buffers; do it on a throw-away copy instead.
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1):
+            cx = self._fwd_bwd(*self._static)
+        with torch.cuda.graph(g2):
+            self._update()
+        self._graphs = (g1, g2)
+        self._loss3 = cx.loss3
+        self._sig = (tuple(images.shape), tuple(target.shape))
+
+    def step(self, images, target):
+        if not self.use_graph:
+            return self.eager(images, target)
+        sig = (tuple(images.shape), tuple(target.shape))
+        if self._graphs is None or sig != self._sig:
+            # capture needs a warm-up forward/backward that must not disturb model state
+            st = self.model.engine.store
+            snap = (st.bufs.clone(), st.nbt.clone())
+            self._capture(images, target)
+            st.bufs.copy_(snap[0]); st.nbt.copy_(snap[1])
+        self.opt.sync_hyperparams()
+        self._static[0].copy_(images, non_blocking=True)
+        self._static[1].copy_(target, non_blocking=True)
+        self._graphs[0].replay()
+        self._allreduce()
+        self._graphs[1].replay()
+        return self._loss3
+
+
+def train_single_epoch_krn(epoch, cfg, model, data_loader, optimizer,
+                           writer, device, styleAugmentor=None, scaler=None):
+    """Same signature and behaviour as reference trainer.py:41-112 (scaler is accepted; bf16 needs no
+    loss scaling so it is only used as the 'mixed precision on' flag)."""
+    training_time_meter = AverageMeter('ms')
+    loss_x_meter = AverageMeter('-')
+    loss_y_meter = AverageMeter('-')
+    model.train()
+    for pg in optimizer.param_groups:
+        lr = pg['lr']
+    stepper = getattr(model, '_train_step', None)
+    if stepper is None or stepper.opt is not optimizer:
+        stepper = KRNTrainStep(model, optimizer, use_graph=getattr(cfg, 'use_graph', True))
+        model._train_step = stepper
+    pending = None
+    for idx, (images, target) in enumerate(data_loader):
+        start = time.time()
+        B = images.shape[0]
+        images = images.to(device, non_blocking=True).float().contiguous()
+        target = target.to(device, non_blocking=True).float().contiguous()
+        if styleAugmentor is not None and random.random() < cfg.texture_ratio:
+            images = styleAugmentor(images)
+        loss3 = stepper.step(images, target)
+        # read the PREVIOUS iteration's losses (already complete) instead of syncing on this one
+        if pending is not None:
+            l3, pb = pending
+            loss_x_meter.update(float(l3[1]), pb)
+            loss_y_meter.update(float(l3[2]), pb)
+        host = torch.empty(3, pin_memory=True)
+        host.copy_(loss3, non_blocking=True)
+        ev = torch.cuda.Event(); ev.record()
+        pending = (host, B)
+        training_time_meter.update((time.time() - start) * 1000, B)
+        report_progress(epoch=epoch, lr=lr, epoch_iter=idx + 1, epoch_size=len(data_loader),
+                        time=training_time_meter, is_train=True, loss_x=loss_x_meter, loss_y=loss_y_meter)
+    if pending is not None:
+        torch.cuda.synchronize()
+        loss_x_meter.update(float(pending[0][1]), pending[1])
+        loss_y_meter.update(float(pending[0][2]), pending[1])
+    if writer is not None:
+        writer.add_scalar('train/loss_x', loss_x_meter.avg, epoch)
+        writer.add_scalar('train/loss_y', loss_y_meter.avg, epoch)

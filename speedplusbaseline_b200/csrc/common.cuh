@@ -1,0 +1,151 @@
+// common.cuh -- shared device helpers for libb200sp (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "b200sp.h"
+
+extern long long g_b200sp_launches;      // defined in misc.cu
+#define B200SP_COUNT_LAUNCH() (++g_b200sp_launches)
+#define B200SP_RETURN_LAST()  do { cudaError_t e__ = cudaGetLastError(); return (int)e__; } while (0)
+
+#define NUM_SMS 148
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float act_fwd(float z, int act) {
+    switch (act) {
+        case B200SP_ACT_RELU:    return fmaxf(z, 0.f);
+        case B200SP_ACT_RELU6:   return fminf(fmaxf(z, 0.f), 6.f);
+        case B200SP_ACT_LEAKY02: return z > 0.f ? z : 0.2f * z;
+        case B200SP_ACT_SIGMOID: return 1.f / (1.f + __expf(-z));
+        default:                 return z;
+    }
+}
+// derivative of the activation w.r.t. its input z (hardtanh backward: open interval)
+__device__ __forceinline__ float act_bwd(float z, int act) {
+    switch (act) {
+        case B200SP_ACT_RELU:    return z > 0.f ? 1.f : 0.f;
+        case B200SP_ACT_RELU6:   return (z > 0.f && z < 6.f) ? 1.f : 0.f;
+        case B200SP_ACT_LEAKY02: return z > 0.f ? 1.f : 0.2f;
+        default:                 return 1.f;
+    }
+}
+
+// ---- 4-element vector access for float / bf16 storage -------------------------------------
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+    static __device__ __forceinline__ float4 ld(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+    static __device__ __forceinline__ float4 ld_plain(const float* p) { return *reinterpret_cast<const float4*>(p); }
+    static __device__ __forceinline__ void st(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+    static __device__ __forceinline__ void st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+    static __device__ __forceinline__ float ld1(const float* p) { return __ldg(p); }
+    static __device__ __forceinline__ void st1(float* p, float v) { *p = v; }
+};
+template <> struct Vec4<bf16> {
+    static __device__ __forceinline__ float4 ld(const bf16* p) {
+        uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+        __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&u.x);
+        __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&u.y);
+        float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+        return make_float4(fa.x, fa.y, fb.x, fb.y);
+    }
+    static __device__ __forceinline__ float4 ld_plain(const bf16* p) { return ld(p); }
+    static __device__ __forceinline__ void st(bf16* p, float4 v) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&a);
+        u.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(p) = u;
+    }
+    static __device__ __forceinline__ void st2(bf16* p, float a, float b) {
+        *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+    }
+    static __device__ __forceinline__ float ld1(const bf16* p) { return __bfloat162float(*p); }
+    static __device__ __forceinline__ void st1(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+// apply the virtual-tensor transform to 4 consecutive channels starting at c
+__device__ __forceinline__ float4 vt_apply4(const b200sp_vtensor& t, float4 x, float4 x2, int c) {
+    if (t.mode == B200SP_VT_PLAIN) return x;
+    float4 a = ldg4(t.p0 + c), b = ldg4(t.p1 + c);
+    if (t.mode == B200SP_VT_BNACT) {
+        return make_float4(act_fwd(fmaf(x.x, a.x, b.x), t.act), act_fwd(fmaf(x.y, a.y, b.y), t.act),
+                           act_fwd(fmaf(x.z, a.z, b.z), t.act), act_fwd(fmaf(x.w, a.w, b.w), t.act));
+    }
+    float4 d = ldg4(t.p2 + c);
+    return make_float4(fmaf(a.x, x.x, fmaf(b.x, x2.x, d.x)), fmaf(a.y, x.y, fmaf(b.y, x2.y, d.y)),
+                       fmaf(a.z, x.z, fmaf(b.z, x2.z, d.z)), fmaf(a.w, x.w, fmaf(b.w, x2.w, d.w)));
+}
+
+// load 4 consecutive channels of a virtual tensor at flat element offset `off` (channel index c)
+template <typename T>
+__device__ __forceinline__ float4 vt_load4(const b200sp_vtensor& t, size_t off, int c) {
+    float4 x = Vec4<T>::ld(reinterpret_cast<const T*>(t.x) + off);
+    float4 x2 = f4zero();
+    if (t.mode == B200SP_VT_DY) x2 = Vec4<T>::ld(reinterpret_cast<const T*>(t.x2) + off);
+    return vt_apply4(t, x, x2, c);
+}
+
+__device__ __forceinline__ double ld_cg_f64(const double* p) {
+    double v;
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+// ---- BatchNorm "last CTA" finalisers --------------------------------------------------------
+// forward: sums -> scale/shift/mean/rstd, running stats; zeroes the accumulators.
+__device__ __forceinline__ void bn_fwd_finalize_channel(const b200sp_bnfwd& bn, int c, double count) {
+    double s = ld_cg_f64(bn.sum + c), q = ld_cg_f64(bn.sumsq + c);
+    double mean = s / count;
+    double var = q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    double rstd = 1.0 / sqrt(var + (double)bn.eps);
+    float sc = (float)((double)bn.gamma[c] * rstd);
+    bn.scale[c] = sc;
+    bn.shift[c] = (float)((double)bn.beta[c] - mean * (double)bn.gamma[c] * rstd);
+    bn.mean[c] = (float)mean;
+    bn.rstd[c] = (float)rstd;
+    if (bn.running_mean) {
+        double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+        bn.running_mean[c] = (float)((1.0 - bn.momentum) * (double)bn.running_mean[c] + bn.momentum * mean);
+        bn.running_var[c] = (float)((1.0 - bn.momentum) * (double)bn.running_var[c] + bn.momentum * unb);
+    }
+    bn.sum[c] = 0.0;
+    bn.sumsq[c] = 0.0;
+}
+// backward: s1 = sum g, s2 = sum g*xhat  ->  dgamma, dbeta, dy = cA*g + cB*y + cC
+__device__ __forceinline__ void bn_bwd_finalize_channel(const b200sp_bnbwd& bn, int c, double count) {
+    double s1 = ld_cg_f64(bn.s1 + c), s2 = ld_cg_f64(bn.s2 + c);
+    double sc = bn.scale[c], rstd = bn.rstd[c], mean = bn.mean[c];
+    double cB = -sc * rstd * s2 / count;
+    bn.cA[c] = (float)sc;
+    bn.cB[c] = (float)cB;
+    bn.cC[c] = (float)(-sc * s1 / count - cB * mean);
+    bn.dgamma[c] += (float)s2;
+    bn.dbeta[c] += (float)s1;
+    bn.s1[c] = 0.0;
+    bn.s2[c] = 0.0;
+}
+
+// Elect the last CTA of the grid.  Call after this CTA's global atomics.  Returns true in every
+// thread of the last CTA (after which it may read the accumulators with ld.cg).
+__device__ __forceinline__ bool grid_last_cta(uint32_t* ticket, uint32_t total) {
+    __shared__ int s_is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = atomicAdd(ticket, 1u);
+        s_is_last = (t == total - 1u);
+        if (s_is_last) *ticket = 0u;
+    }
+    __syncthreads();
+    bool last = s_is_last != 0;
+    if (last) __threadfence();
+    return last;
+}
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
