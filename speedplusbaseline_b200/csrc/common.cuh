@@ -13,24 +13,29 @@ extern long long g_b200sp_launches;      // defined in misc.cu
 
 typedef __nv_bfloat16 bf16;
 
+// Branch-free activations.  Every supported activation except sigmoid is
+//   act(z) = min(max(z,0) + slope*min(z,0), hi)      relu: (0, inf)  relu6: (0, 6)  leaky: (0.2, inf)  none: (1, inf)
+// so the per-element cost is 4 instructions with two kernel-uniform constants instead of a switch.
+struct ActP { float slope, hi; };
+__device__ __forceinline__ ActP act_params(int act) {
+    ActP a;
+    a.slope = act == B200SP_ACT_NONE ? 1.f : (act == B200SP_ACT_LEAKY02 ? 0.2f : 0.f);
+    a.hi = act == B200SP_ACT_RELU6 ? 6.f : __int_as_float(0x7f800000);
+    return a;
+}
+__device__ __forceinline__ float act_fwd(float z, ActP a) {
+    return fminf(fmaf(a.slope, fminf(z, 0.f), fmaxf(z, 0.f)), a.hi);
+}
+// derivative w.r.t. the pre-activation z (hardtanh backward: open interval)
+__device__ __forceinline__ float act_bwd(float z, ActP a) {
+    const float d = z > 0.f ? 1.f : a.slope;
+    return z < a.hi ? d : 0.f;
+}
 __device__ __forceinline__ float act_fwd(float z, int act) {
-    switch (act) {
-        case B200SP_ACT_RELU:    return fmaxf(z, 0.f);
-        case B200SP_ACT_RELU6:   return fminf(fmaxf(z, 0.f), 6.f);
-        case B200SP_ACT_LEAKY02: return z > 0.f ? z : 0.2f * z;
-        case B200SP_ACT_SIGMOID: return 1.f / (1.f + __expf(-z));
-        default:                 return z;
-    }
+    if (act == B200SP_ACT_SIGMOID) return 1.f / (1.f + __expf(-z));
+    return act_fwd(z, act_params(act));
 }
-// derivative of the activation w.r.t. its input z (hardtanh backward: open interval)
-__device__ __forceinline__ float act_bwd(float z, int act) {
-    switch (act) {
-        case B200SP_ACT_RELU:    return z > 0.f ? 1.f : 0.f;
-        case B200SP_ACT_RELU6:   return (z > 0.f && z < 6.f) ? 1.f : 0.f;
-        case B200SP_ACT_LEAKY02: return z > 0.f ? 1.f : 0.2f;
-        default:                 return 1.f;
-    }
-}
+__device__ __forceinline__ float act_bwd(float z, int act) { return act_bwd(z, act_params(act)); }
 
 // ---- 4-element vector access for float / bf16 storage -------------------------------------
 template <typename T> struct Vec4;
@@ -73,8 +78,9 @@ __device__ __forceinline__ float4 vt_apply4(const b200sp_vtensor& t, float4 x, f
     if (t.mode == B200SP_VT_PLAIN) return x;
     float4 a = ldg4(t.p0 + c), b = ldg4(t.p1 + c);
     if (t.mode == B200SP_VT_BNACT) {
-        return make_float4(act_fwd(fmaf(x.x, a.x, b.x), t.act), act_fwd(fmaf(x.y, a.y, b.y), t.act),
-                           act_fwd(fmaf(x.z, a.z, b.z), t.act), act_fwd(fmaf(x.w, a.w, b.w), t.act));
+        const ActP ap = act_params(t.act);
+        return make_float4(act_fwd(fmaf(x.x, a.x, b.x), ap), act_fwd(fmaf(x.y, a.y, b.y), ap),
+                           act_fwd(fmaf(x.z, a.z, b.z), ap), act_fwd(fmaf(x.w, a.w, b.w), ap));
     }
     float4 d = ldg4(t.p2 + c);
     return make_float4(fmaf(a.x, x.x, fmaf(b.x, x2.x, d.x)), fmaf(a.y, x.y, fmaf(b.y, x2.y, d.y)),

@@ -23,21 +23,22 @@ __device__ __forceinline__ float4 f4fma(float4 a, float4 b, float4 c) {
 }
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float4 f4mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
-__device__ __forceinline__ float4 f4act(float4 z, int act) {
+__device__ __forceinline__ float4 f4act(float4 z, ActP act) {
     return make_float4(act_fwd(z.x, act), act_fwd(z.y, act), act_fwd(z.z, act), act_fwd(z.w, act));
 }
-__device__ __forceinline__ float4 f4actbwd(float4 z, int act) {
+__device__ __forceinline__ float4 f4actbwd(float4 z, ActP act) {
     return make_float4(act_bwd(z.x, act), act_bwd(z.y, act), act_bwd(z.z, act), act_bwd(z.w, act));
 }
 
 // per-thread copy of a virtual tensor's channel parameters (4 channels)
 struct VtParams {
     float4 p0, p1, p2;
-    int mode, act;
+    int mode;
+    ActP act;
 };
 __device__ __forceinline__ VtParams vt_params(const b200sp_vtensor& t, int c) {
     VtParams p;
-    p.mode = t.mode; p.act = t.act;
+    p.mode = t.mode; p.act = act_params(t.act);
     p.p0 = p.p1 = p.p2 = f4zero();
     if (t.mode != B200SP_VT_PLAIN) { p.p0 = ldg4(t.p0 + c); p.p1 = ldg4(t.p1 + c); }
     if (t.mode == B200SP_VT_DY) p.p2 = ldg4(t.p2 + c);
@@ -53,22 +54,27 @@ __device__ __forceinline__ float4 vt_fetch(const b200sp_vtensor& t, const VtPara
 }
 
 // ------------------------------------------------------------------------------------------------
+// Forward.  Each thread owns 4 channels and produces OW consecutive outputs per group from a
+// 3 x ((OW-1)*S+3) register tile whose loads are all issued before the first FMA (memory-level
+// parallelism: 15-18 independent 16-byte loads per thread in flight).
 template <typename T, int S>
-__global__ void __launch_bounds__(DW_NT) dw_fwd_kernel(const b200sp_vtensor x, const float* __restrict__ w9c, T* __restrict__ y,
-                                                       const b200sp_bnfwd bn, const int has_bn, const DwGeom gm) {
+__global__ void __launch_bounds__(DW_NT, 2) dw_fwd_kernel(const b200sp_vtensor x, const float* __restrict__ w9c, T* __restrict__ y,
+                                                          const b200sp_bnfwd bn, const int has_bn, const DwGeom gm) {
+    constexpr int OW = S == 1 ? 4 : 2;
+    constexpr int NC = (OW - 1) * S + 3;
+    __shared__ __align__(16) float s_w[9][DW_NT];
     __shared__ float s_sum[DW_NT], s_sq[DW_NT];
     const int tid = threadIdx.x;
     const int cl = tid % gm.CB, sl = tid / gm.CB;
     const bool active = sl < gm.SPC;
-    const int c = (blockIdx.y * gm.CB + cl) * 4;
+    const int cbase = blockIdx.y * gm.CB * 4;
+    const int c = cbase + cl * 4;
+    for (int t = 0; t < 9; ++t) s_w[t][tid] = (tid < gm.CB * 4) ? __ldg(w9c + (size_t)t * gm.C + cbase + tid) : 0.f;
     s_sum[tid] = 0.f; s_sq[tid] = 0.f;
     __syncthreads();
 
     float4 lsum = f4zero(), lsq = f4zero();
     if (active) {
-        float4 w[9];
-#pragma unroll
-        for (int t = 0; t < 9; ++t) w[t] = ldg4(w9c + (size_t)t * gm.C + c);
         const VtParams xp = vt_params(x, c);
         for (long long sg = blockIdx.x; sg * gm.SPC < gm.nstrips; sg += gridDim.x) {
             const long long strip = sg * gm.SPC + sl;
@@ -78,38 +84,31 @@ __global__ void __launch_bounds__(DW_NT) dw_fwd_kernel(const b200sp_vtensor x, c
             const int ho = (int)(t2 % gm.Ho), b = (int)(t2 / gm.Ho);
             const int wo0 = seg * gm.SEGW, wo1 = min(gm.Wo, wo0 + gm.SEGW);
             const int hi0 = ho * S - 1;
-            float4 win[3][3];
-            auto load_col = [&](int wi, int slot) {
-#pragma unroll
-                for (int kh = 0; kh < 3; ++kh) {
-                    const int hi = hi0 + kh;
-                    float4 v = f4zero();
-                    if (hi >= 0 && hi < gm.H && wi >= 0 && wi < gm.W)
-                        v = vt_fetch<T>(x, xp, ((size_t)(b * gm.H + hi) * gm.W + wi) * gm.C + c);
-                    win[kh][slot] = v;
-                }
-            };
-            if (S == 1) { load_col(wo0 - 1, 1); load_col(wo0, 2); }
-            else        { load_col(wo0 * 2 - 1, 2); }
-            for (int wo = wo0; wo < wo1; ++wo) {
-                if (S == 1) {
-#pragma unroll
-                    for (int kh = 0; kh < 3; ++kh) { win[kh][0] = win[kh][1]; win[kh][1] = win[kh][2]; }
-                    load_col(wo + 1, 2);
-                } else {
-#pragma unroll
-                    for (int kh = 0; kh < 3; ++kh) win[kh][0] = win[kh][2];
-                    load_col(wo * 2, 1);
-                    load_col(wo * 2 + 1, 2);
-                }
-                float4 acc = f4zero();
+            for (int wg = wo0; wg < wo1; wg += OW) {
+                float4 in[3][NC];
 #pragma unroll
                 for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-                    for (int kw = 0; kw < 3; ++kw) acc = f4fma(win[kh][kw], w[kh * 3 + kw], acc);
-                Vec4<T>::st(y + ((size_t)(b * gm.Ho + ho) * gm.Wo + wo) * gm.C + c, acc);
-                lsum = f4add(lsum, acc);
-                lsq = f4fma(acc, acc, lsq);
+                    for (int j = 0; j < NC; ++j) {
+                        const int hi = hi0 + kh, wi = wg * S - 1 + j;
+                        float4 v = f4zero();
+                        if (hi >= 0 && hi < gm.H && wi >= 0 && wi < gm.W)
+                            v = vt_fetch<T>(x, xp, ((size_t)(b * gm.H + hi) * gm.W + wi) * gm.C + c);
+                        in[kh][j] = v;
+                    }
+#pragma unroll
+                for (int o = 0; o < OW; ++o) {
+                    if (wg + o >= wo1) break;
+                    float4 acc = f4zero();
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                        for (int kw = 0; kw < 3; ++kw)
+                            acc = f4fma(in[kh][o * S + kw], *reinterpret_cast<const float4*>(&s_w[kh * 3 + kw][cl * 4]), acc);
+                    Vec4<T>::st(y + ((size_t)(b * gm.Ho + ho) * gm.Wo + wg + o) * gm.C + c, acc);
+                    lsum = f4add(lsum, acc);
+                    lsq = f4fma(acc, acc, lsq);
+                }
             }
         }
     }
@@ -122,22 +121,43 @@ __global__ void __launch_bounds__(DW_NT) dw_fwd_kernel(const b200sp_vtensor x, c
     }
     __syncthreads();
     if (tid < gm.CB * 4) {
-        const int cc = blockIdx.y * gm.CB * 4 + tid;
-        atomicAdd(bn.sum + cc, (double)s_sum[tid]);
-        atomicAdd(bn.sumsq + cc, (double)s_sq[tid]);
+        atomicAdd(bn.sum + cbase + tid, (double)s_sum[tid]);
+        atomicAdd(bn.sumsq + cbase + tid, (double)s_sq[tid]);
     }
     if (grid_last_cta(bn.ticket, gridDim.x * gridDim.y))
         for (int cc = tid; cc < gm.C; cc += DW_NT) bn_fwd_finalize_channel(bn, cc, gm.count);
 }
 
 // ------------------------------------------------------------------------------------------------
-// Backward.  Threads walk INPUT pixels (hi, wi).  dy is a virtual tensor in output coordinates.
+// Backward.  Threads walk INPUT pixels (hi, wi) in groups (2 for stride 1, 4 for stride 2); the dy
+// values the group needs are fetched as one register tile up front.  dy is a virtual tensor in
+// output coordinates (BatchNorm backward folded into the load).
+struct DwBwdCtx {
+    float4 sc, sh;
+    bool has_bn, do_stats, same_src;
+    ActP act;
+};
+
+template <typename T>
+__device__ __forceinline__ void dw_bwd_pixel(const b200sp_vtensor& x, const VtParams& xp, const b200sp_bnbwd& bn, const DwBwdCtx& cx,
+                                             const T* __restrict__ skip, T* __restrict__ g_in, size_t off, float4 dg,
+                                             float4 yin, float4 a_known, float4& ls1, float4& ls2) {
+    (void)x; (void)xp; (void)a_known;
+    if (skip) dg = f4add(dg, Vec4<T>::ld(skip + off));
+    if (cx.has_bn) {
+        const float4 z = f4fma(yin, cx.sc, cx.sh);
+        dg = f4mul(dg, f4actbwd(z, cx.act));
+        if (cx.do_stats) { ls1 = f4add(ls1, dg); ls2 = f4fma(dg, yin, ls2); }
+    }
+    if (g_in) Vec4<T>::st(g_in + off, dg);
+}
+
 template <typename T, int S>
-__global__ void __launch_bounds__(DW_NT) dw_bwd_kernel(const b200sp_vtensor dy, const b200sp_vtensor x, const float* __restrict__ w9c,
-                                                       const T* __restrict__ skip, T* __restrict__ g_in, float* __restrict__ dw9c,
-                                                       const b200sp_bnbwd bn, const int has_bn, const DwGeom gm) {
+__global__ void __launch_bounds__(DW_NT, 1) dw_bwd_kernel(const b200sp_vtensor dy, const b200sp_vtensor x, const float* __restrict__ w9c,
+                                                          const T* __restrict__ skip, T* __restrict__ g_in, float* __restrict__ dw9c,
+                                                          const b200sp_bnbwd bn, const int has_bn, const DwGeom gm) {
     __shared__ __align__(16) float s_w[9][DW_NT];       // weights of this CTA's channels  [tap][cl*4+j]
-    __shared__ float s_dw[9][DW_NT];      // wgrad accumulators
+    __shared__ float s_dw[9][DW_NT];                    // wgrad accumulators
     __shared__ float s_s1[DW_NT], s_s2[DW_NT];
     const int tid = threadIdx.x;
     const int cl = tid % gm.CB, sl = tid / gm.CB;
@@ -151,18 +171,27 @@ __global__ void __launch_bounds__(DW_NT) dw_bwd_kernel(const b200sp_vtensor dy, 
     s_s1[tid] = 0.f; s_s2[tid] = 0.f;
     __syncthreads();
 
-    const bool do_stats = has_bn && bn.s1 != nullptr;
+    DwBwdCtx cx;
+    cx.has_bn = has_bn != 0;
+    cx.do_stats = cx.has_bn && bn.s1 != nullptr;
+    cx.act = act_params(bn.act);
+    cx.sc = make_float4(1.f, 1.f, 1.f, 1.f); cx.sh = f4zero();
     if (active) {
         const VtParams dp = vt_params(dy, c);
         const VtParams xp = vt_params(x, c);
-        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = f4zero(), mu = f4zero(), rs = f4zero();
-        if (has_bn && bn.scale) { sc = ldg4(bn.scale + c); sh = ldg4(bn.shift + c); }
-        if (do_stats) { mu = ldg4(bn.mean + c); rs = ldg4(bn.rstd + c); }
-        const bool same_src = has_bn && x.mode == B200SP_VT_BNACT && x.x == bn.y;
+        if (cx.has_bn && bn.scale) { cx.sc = ldg4(bn.scale + c); cx.sh = ldg4(bn.shift + c); }
+        cx.same_src = cx.has_bn && x.mode == B200SP_VT_BNACT && x.x == bn.y;
         float4 dwacc[9];
 #pragma unroll
         for (int t = 0; t < 9; ++t) dwacc[t] = f4zero();
-        float4 ls1 = f4zero(), ls2 = f4zero();
+        float4 ls1 = f4zero(), ls2 = f4zero();       // sum g, sum g*y  (xhat applied at flush)
+        const T* ybn = reinterpret_cast<const T*>(bn.y);
+        auto wtap = [&](int tap) { return *reinterpret_cast<const float4*>(&s_w[tap][cl * 4]); };
+        // value of the conv input (for wgrad) at element offset `off`, given the raw BN input yin
+        auto in_val = [&](size_t off, float4 yin) {
+            if (cx.same_src) return f4act(f4fma(yin, cx.sc, cx.sh), xp.act);
+            return vt_fetch<T>(x, xp, off);
+        };
 
         for (long long sg = blockIdx.x; sg * gm.SPC < gm.nstrips; sg += gridDim.x) {
             const long long strip = sg * gm.SPC + sl;
@@ -171,73 +200,102 @@ __global__ void __launch_bounds__(DW_NT) dw_bwd_kernel(const b200sp_vtensor dy, 
             const long long t2 = strip / gm.nseg;
             const int hi = (int)(t2 % gm.H), b = (int)(t2 / gm.H);
             const int wi0 = seg * gm.SEGW, wi1 = min(gm.W, wi0 + gm.SEGW);
-
-            float4 win[3][3];   // S==1 only: dy at rows hi-1..hi+1, cols wi-1..wi+1
-            auto load_col = [&](int wo, int slot) {
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    const int ho = hi - 1 + r;
-                    float4 v = f4zero();
-                    if (ho >= 0 && ho < gm.Ho && wo >= 0 && wo < gm.Wo)
-                        v = vt_fetch<T>(dy, dp, ((size_t)(b * gm.Ho + ho) * gm.Wo + wo) * gm.C + c);
-                    win[r][slot] = v;
-                }
-            };
-            if (S == 1) { load_col(wi0 - 1, 1); load_col(wi0, 2); }
-
-            for (int wi = wi0; wi < wi1; ++wi) {
-                const size_t off = ((size_t)(b * gm.H + hi) * gm.W + wi) * gm.C + c;
-                // ---- value of the conv input at this pixel (for wgrad) and its pre-activation z
-                float4 yin = f4zero(), z = f4zero(), a;
-                if (has_bn) { yin = Vec4<T>::ld(reinterpret_cast<const T*>(bn.y) + off); z = f4fma(yin, sc, sh); }
-                if (same_src) a = f4act(z, xp.act);
-                else          a = vt_fetch<T>(x, xp, off);
-
-                float4 dg = f4zero();
-                if (S == 1) {
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) { win[r][0] = win[r][1]; win[r][1] = win[r][2]; }
-                    load_col(wi + 1, 2);
-                    // output (hi+dh, wi+dw) used tap (kh,kw) = (1-dh, 1-dw);  win[r][s] holds dh=r-1, dw=s-1
+            if (S == 1) {
+                constexpr int OW = 2, NC = OW + 2;
+                for (int wg = wi0; wg < wi1; wg += OW) {
+                    float4 D[3][NC];
 #pragma unroll
                     for (int r = 0; r < 3; ++r)
 #pragma unroll
-                        for (int s = 0; s < 3; ++s) {
-                            const int tap = (2 - r) * 3 + (2 - s);
-                            const float4 wv = *reinterpret_cast<const float4*>(&s_w[tap][cl * 4]);
-                            dg = f4fma(win[r][s], wv, dg);
-                            dwacc[tap] = f4fma(a, win[r][s], dwacc[tap]);
+                        for (int j = 0; j < NC; ++j) {
+                            const int ho = hi - 1 + r, wo = wg - 1 + j;
+                            float4 v = f4zero();
+                            if (ho >= 0 && ho < gm.Ho && wo >= 0 && wo < gm.Wo)
+                                v = vt_fetch<T>(dy, dp, ((size_t)(b * gm.Ho + ho) * gm.Wo + wo) * gm.C + c);
+                            D[r][j] = v;
                         }
-                } else {
+                    float4 yin[OW], av[OW];
+                    size_t offs[OW];
 #pragma unroll
-                    for (int kh = 0; kh < 3; ++kh) {
-                        const int th = hi + 1 - kh;
-                        if (th < 0 || (th & 1)) continue;
-                        const int ho = th >> 1;
-                        if (ho >= gm.Ho) continue;
+                    for (int o = 0; o < OW; ++o) {
+                        offs[o] = ((size_t)(b * gm.H + hi) * gm.W + min(wg + o, gm.W - 1)) * gm.C + c;
+                        yin[o] = cx.has_bn ? Vec4<T>::ld(ybn + offs[o]) : f4zero();
+                        av[o] = in_val(offs[o], yin[o]);
+                    }
 #pragma unroll
-                        for (int kw = 0; kw < 3; ++kw) {
-                            const int tw = wi + 1 - kw;
-                            if (tw < 0 || (tw & 1)) continue;
-                            const int wo = tw >> 1;
-                            if (wo >= gm.Wo) continue;
-                            const float4 d = vt_fetch<T>(dy, dp, ((size_t)(b * gm.Ho + ho) * gm.Wo + wo) * gm.C + c);
-                            const float4 wv = *reinterpret_cast<const float4*>(&s_w[kh * 3 + kw][cl * 4]);
-                            dg = f4fma(d, wv, dg);
-                            dwacc[kh * 3 + kw] = f4fma(a, d, dwacc[kh * 3 + kw]);
-                        }
+                    for (int o = 0; o < OW; ++o) {
+                        if (wg + o >= wi1) break;
+                        float4 dg = f4zero();
+                        // output (hi+dh, wi+dw) used tap (kh,kw) = (1-dh, 1-dw);  D[r][o+s] holds dh=r-1, dw=s-1
+#pragma unroll
+                        for (int r = 0; r < 3; ++r)
+#pragma unroll
+                            for (int sx = 0; sx < 3; ++sx) {
+                                const int tap = (2 - r) * 3 + (2 - sx);
+                                dg = f4fma(D[r][o + sx], wtap(tap), dg);
+                                dwacc[tap] = f4fma(av[o], D[r][o + sx], dwacc[tap]);
+                            }
+                        dw_bwd_pixel<T>(x, xp, bn, cx, skip, g_in, offs[o], dg, yin[o], av[o], ls1, ls2);
                     }
                 }
-                if (skip) dg = f4add(dg, Vec4<T>::ld(skip + off));
-                if (has_bn) {
-                    dg = f4mul(dg, f4actbwd(z, bn.act));
-                    if (do_stats) {
-                        ls1 = f4add(ls1, dg);
-                        ls2 = make_float4(fmaf(dg.x, (yin.x - mu.x) * rs.x, ls2.x), fmaf(dg.y, (yin.y - mu.y) * rs.y, ls2.y),
-                                          fmaf(dg.z, (yin.z - mu.z) * rs.z, ls2.z), fmaf(dg.w, (yin.w - mu.w) * rs.w, ls2.w));
+            } else {
+                // stride 2: 4 input pixels starting at an even column; contributing outputs are rows
+                // {hi/2} (hi even, kh=1) or {(hi+1)/2 (kh=0), (hi-1)/2 (kh=2)} (hi odd), cols wi0/2 .. wi0/2+2
+                const bool odd = hi & 1;
+                const int ho0 = odd ? (hi + 1) >> 1 : hi >> 1, ho1 = (hi - 1) >> 1;
+                for (int wg = wi0; wg < wi1; wg += 4) {
+                    float4 D[2][3];
+#pragma unroll
+                    for (int r = 0; r < 2; ++r)
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            const int ho = r == 0 ? ho0 : ho1, wo = (wg >> 1) + j;
+                            float4 v = f4zero();
+                            if ((r == 0 || odd) && ho < gm.Ho && wo < gm.Wo)
+                                v = vt_fetch<T>(dy, dp, ((size_t)(b * gm.Ho + ho) * gm.Wo + wo) * gm.C + c);
+                            D[r][j] = v;
+                        }
+                    float4 yin[4], av[4];
+                    size_t offs[4];
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) {
+                        offs[o] = ((size_t)(b * gm.H + hi) * gm.W + min(wg + o, gm.W - 1)) * gm.C + c;
+                        yin[o] = cx.has_bn ? Vec4<T>::ld(ybn + offs[o]) : f4zero();
+                        av[o] = in_val(offs[o], yin[o]);
+                    }
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) {
+                        if (wg + o >= wi1) break;
+                        float4 dg = f4zero();
+                        // taps: even pixel -> (kw=1, j=o/2); odd pixel -> (kw=0, j=(o+1)/2) and (kw=2, j=(o-1)/2)
+#pragma unroll
+                        for (int r = 0; r < 2; ++r) {
+                            if (odd) {                         // r=0 -> kh=0, r=1 -> kh=2
+                                const int kh = r * 2;
+                                if ((o & 1) == 0) {
+                                    dg = f4fma(D[r][o / 2], wtap(kh * 3 + 1), dg);
+                                    if (r == 0) dwacc[1] = f4fma(av[o], D[r][o / 2], dwacc[1]); else dwacc[7] = f4fma(av[o], D[r][o / 2], dwacc[7]);
+                                } else {
+                                    dg = f4fma(D[r][(o + 1) / 2], wtap(kh * 3 + 0), dg);
+                                    dg = f4fma(D[r][(o - 1) / 2], wtap(kh * 3 + 2), dg);
+                                    if (r == 0) { dwacc[0] = f4fma(av[o], D[r][(o + 1) / 2], dwacc[0]); dwacc[2] = f4fma(av[o], D[r][(o - 1) / 2], dwacc[2]); }
+                                    else        { dwacc[6] = f4fma(av[o], D[r][(o + 1) / 2], dwacc[6]); dwacc[8] = f4fma(av[o], D[r][(o - 1) / 2], dwacc[8]); }
+                                }
+                            } else if (r == 0) {               // kh = 1
+                                if ((o & 1) == 0) {
+                                    dg = f4fma(D[0][o / 2], wtap(4), dg);
+                                    dwacc[4] = f4fma(av[o], D[0][o / 2], dwacc[4]);
+                                } else {
+                                    dg = f4fma(D[0][(o + 1) / 2], wtap(3), dg);
+                                    dg = f4fma(D[0][(o - 1) / 2], wtap(5), dg);
+                                    dwacc[3] = f4fma(av[o], D[0][(o + 1) / 2], dwacc[3]);
+                                    dwacc[5] = f4fma(av[o], D[0][(o - 1) / 2], dwacc[5]);
+                                }
+                            }
+                        }
+                        dw_bwd_pixel<T>(x, xp, bn, cx, skip, g_in, offs[o], dg, yin[o], av[o], ls1, ls2);
                     }
                 }
-                if (g_in) Vec4<T>::st(g_in + off, dg);
             }
         }
 #pragma unroll
@@ -245,22 +303,24 @@ __global__ void __launch_bounds__(DW_NT) dw_bwd_kernel(const b200sp_vtensor dy, 
             atomicAdd(&s_dw[t][cl * 4 + 0], dwacc[t].x); atomicAdd(&s_dw[t][cl * 4 + 1], dwacc[t].y);
             atomicAdd(&s_dw[t][cl * 4 + 2], dwacc[t].z); atomicAdd(&s_dw[t][cl * 4 + 3], dwacc[t].w);
         }
-        if (do_stats) {
+        if (cx.do_stats) {
+            // s2 = sum g*xhat = rstd * (sum g*y - mean * sum g)
+            const float4 mu = ldg4(bn.mean + c), rs = ldg4(bn.rstd + c);
             atomicAdd(&s_s1[cl * 4 + 0], ls1.x); atomicAdd(&s_s1[cl * 4 + 1], ls1.y);
             atomicAdd(&s_s1[cl * 4 + 2], ls1.z); atomicAdd(&s_s1[cl * 4 + 3], ls1.w);
-            atomicAdd(&s_s2[cl * 4 + 0], ls2.x); atomicAdd(&s_s2[cl * 4 + 1], ls2.y);
-            atomicAdd(&s_s2[cl * 4 + 2], ls2.z); atomicAdd(&s_s2[cl * 4 + 3], ls2.w);
+            atomicAdd(&s_s2[cl * 4 + 0], rs.x * (ls2.x - mu.x * ls1.x)); atomicAdd(&s_s2[cl * 4 + 1], rs.y * (ls2.y - mu.y * ls1.y));
+            atomicAdd(&s_s2[cl * 4 + 2], rs.z * (ls2.z - mu.z * ls1.z)); atomicAdd(&s_s2[cl * 4 + 3], rs.w * (ls2.w - mu.w * ls1.w));
         }
     }
     __syncthreads();
     if (tid < gm.CB * 4) {
         for (int t = 0; t < 9; ++t) atomicAdd(dw9c + (size_t)t * gm.C + cbase + tid, s_dw[t][tid]);
-        if (do_stats) {
+        if (cx.do_stats) {
             atomicAdd(bn.s1 + cbase + tid, (double)s_s1[tid]);
             atomicAdd(bn.s2 + cbase + tid, (double)s_s2[tid]);
         }
     }
-    if (do_stats && grid_last_cta(bn.ticket, gridDim.x * gridDim.y))
+    if (cx.do_stats && grid_last_cta(bn.ticket, gridDim.x * gridDim.y))
         for (int cc = tid; cc < gm.C; cc += DW_NT) bn_bwd_finalize_channel(bn, cc, gm.count);
 }
 
@@ -280,7 +340,9 @@ int dw_geom(DwGeom& gm, dim3& grid, int B, int H, int W, int C, int stride, bool
     const int gy = C4 / cb;
     long long passes = (gm.nstrips + gm.SPC - 1) / gm.SPC;
     long long cap = (NUM_SMS * 8 + gy - 1) / gy;
-    grid = dim3((unsigned)(passes < cap ? passes : cap), gy, 1);
+    long long per = (passes + cap - 1) / cap;              // passes per CTA, balanced
+    if (per < 1) per = 1;
+    grid = dim3((unsigned)((passes + per - 1) / per), gy, 1);
     if (grid.x == 0) grid.x = 1;
     return 0;
 }

@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(NT, 2) gemm_kernel(const GemmArgs g) {
 
         // ------------------------------ epilogue ------------------------------
         T* out = reinterpret_cast<T*>(g.out);
+        const ActP oact = act_params(EPI == EPI_FWD ? g.out_act : g.bnb.act);
 #pragma unroll
         for (int ni = 0; ni < NI; ++ni) {
             const int col = q0 + wn * (8 * NI) + ni * 8 + 2 * tq;
@@ -202,8 +203,8 @@ __global__ void __launch_bounds__(NT, 2) gemm_kernel(const GemmArgs g) {
                     float v0 = acc[mi][ni][h * 2], v1 = acc[mi][ni][h * 2 + 1];
                     const size_t off = (size_t)row * g.Q + col;
                     if (EPI == EPI_FWD) {
-                        v0 = act_fwd(v0 + b0, g.out_act);
-                        v1 = act_fwd(v1 + b1, g.out_act);
+                        v0 = act_fwd(v0 + b0, oact);
+                        v1 = act_fwd(v1 + b1, oact);
                         if (ok) {
                             Vec4<T>::st2(out + off, v0, v1);
                             if (g.has_bnf) { csum[ni][0] += v0; csum[ni][1] += v1; csq[ni][0] += v0 * v0; csq[ni][1] += v1 * v1; }
@@ -218,8 +219,8 @@ __global__ void __launch_bounds__(NT, 2) gemm_kernel(const GemmArgs g) {
                             if (g.has_bnb) {
                                 const T* yp = reinterpret_cast<const T*>(g.bnb.y) + off;
                                 float y0 = Vec4<T>::ld1(yp), y1 = Vec4<T>::ld1(yp + 1);
-                                v0 *= act_bwd(fmaf(y0, sc0, sh0), g.bnb.act);
-                                v1 *= act_bwd(fmaf(y1, sc1, sh1), g.bnb.act);
+                                v0 *= act_bwd(fmaf(y0, sc0, sh0), oact);
+                                v1 *= act_bwd(fmaf(y1, sc1, sh1), oact);
                                 if (g.bnb.s1) {
                                     csum[ni][0] += v0; csum[ni][1] += v1;
                                     csq[ni][0] += v0 * (y0 - mu0) * rs0; csq[ni][1] += v1 * (y1 - mu1) * rs1;

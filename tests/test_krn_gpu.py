@@ -1,0 +1,183 @@
+"""Model-level parity of the CUDA KRN path against the oracle / the reference-generated golden files.
+
+Tolerances.  Eval-mode logits: BASELINE.json's bar, rtol 1e-3 (+ atol 1e-3*max|ref|, SURVEY 8c: random-init
+logits cross zero).  Train mode: batch-statistic BatchNorm on tiny batches is chaotic -- torch fp32 and
+torch fp64 themselves disagree by ~1.5e-2 in per-tensor gradient L2 (SURVEY 7 "Hard parts") -- so the
+CUDA path is required to sit within 3x of the fp32 oracle's own distance from the float64 oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import krn as okrn, synth, steps
+from kutil import rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(sd, **kw):
+    from speedplusbaseline_b200.nets.park2019 import KeypointRegressionNet
+    m = KeypointRegressionNet(11, device='cuda:0', **kw)
+    m.load_state_dict(sd)
+    return m
+
+
+def test_eval_logits_match_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'krn_eval_b2.npz'))
+    sd = synth.synth_state_dict(okrn.krn_shapes(), 2021)
+    m = _model(sd).eval()
+    xc, yc = m(synth.synth_images(2).cuda())
+    assert not xc.is_cuda                                      # park2019.py:165 returns CPU tensors
+    ref = np.concatenate([g['xc'], g['yc']], 1)
+    got = np.concatenate([xc.numpy(), yc.numpy()], 1)
+    np.testing.assert_allclose(got, ref, rtol=1e-3, atol=1e-3 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize('B', [1, 3])
+def test_eval_logits_match_oracle_ragged_batch(B):
+    sd = synth.synth_state_dict(okrn.krn_shapes(), 7)
+    x = synth.synth_images(B, seed=5)
+    with torch.no_grad():
+        xr, yr = okrn.krn_forward({k: v.clone() for k, v in sd.items()}, x)
+    xc, yc = _model(sd).eval()(x.cuda())
+    tol = 1e-3 * float(torch.cat([xr, yr]).abs().max())
+    assert torch.allclose(xc, xr, rtol=1e-3, atol=tol) and torch.allclose(yc, yr, rtol=1e-3, atol=tol)
+
+
+def test_train_forward_every_layer():
+    B = 4
+    sd = synth.synth_state_dict(okrn.krn_shapes(), 2021)
+    x, y = synth.synth_images(B), synth.synth_keypoints(B)
+    sdo = {k: v.clone().double() if v.is_floating_point() else v.clone() for k, v in sd.items()}
+    taps = {}
+    with torch.no_grad():
+        taps['logits'] = okrn.krn_logits(sdo, x.double(), True, taps=taps)[1]
+    m = _model(sd).train()
+    cx = m.engine.forward(x.cuda(), y.cuda(), train=True)
+    torch.cuda.synchronize()
+    names = {'base.0.0': 'stem', 'extras.2.conv.0': 'xr'}
+    for b in m.engine.blocks:
+        i, j = b['idx'], (0 if b['t'] == 1 else 1)
+        if b['t'] != 1:
+            names['base.%d.conv.0.0' % i] = 'e%d' % i
+        names['base.%d.conv.%d.0' % (i, j)] = 'd%d' % i
+        names['base.%d.conv.%d' % (i, j + 1)] = 'p%d' % i
+    for e in (0, 1, 3):
+        names['extras.%d.conv.0' % e] = 'xd%d' % e
+        names['extras.%d.conv.3' % e] = 'xp%d' % e
+    for k, n in names.items():
+        assert rel(cx.Y[n].permute(0, 3, 1, 2), taps[k]) < 5e-4, k
+    assert rel(cx.logits, taps['logits']) < 5e-4
+    sdm = m.state_dict()
+    for k in sd:
+        if 'running' in k:
+            assert rel(sdm[k], sdo[k]) < 1e-4, k
+        if k.endswith('num_batches_tracked'):
+            assert int(sdm[k]) == 1
+
+
+def _oracle_step(sd, x, y, dt):
+    s = {k: (v.clone().to(dt) if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    st = steps.new_state(s)
+    return steps.krn_train_step(s, st, x.to(dt), y.to(dt)), s
+
+
+@pytest.mark.parametrize('B', [4, 6])
+def test_train_step_within_fp32_noise_of_float64_oracle(B):
+    from speedplusbaseline_b200.optim import FusedAdamW
+    sd = synth.synth_state_dict(okrn.krn_shapes(), 2021)
+    x, y = synth.synth_images(B), synth.synth_keypoints(B)
+    r64, s64 = _oracle_step(sd, x, y, torch.float64)
+    r32, s32 = _oracle_step(sd, x, y, torch.float32)
+    m = _model(sd).train()
+    opt = FusedAdamW(m._store, m.parameters(), lr=1e-3, betas=(0.9, 0.999), weight_decay=0.01, clip_mode=1)
+    opt.zero_grad()
+    loss, sm = m(x.cuda(), y.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - r64['loss']) <= max(1e-4 * abs(r64['loss']), 3 * abs(r32['loss'] - r64['loss']))
+    assert abs(sm['loss_x'] - r64['loss_x']) <= 2e-4 * abs(r64['loss_x'])
+    gd = m.grad_dict()
+    gn = r64['grad_norm']
+    worst = 0.0
+    for k, g64 in r64['grads'].items():
+        if float(g64.norm()) < 1e-3 * gn:
+            # numerically-zero gradients (e.g. the beta of a BN that feeds a conv+BN) carry no signal
+            assert float((gd[k].double().cpu() - g64).norm()) < 1e-3 * gn, k
+            continue
+        e_cuda, e_f32 = rel(gd[k], g64), rel(r32['grads'][k], g64)
+        worst = max(worst, e_cuda / max(e_f32, 1e-4))
+        assert e_cuda <= 3.0 * e_f32 + 1e-4, (k, e_cuda, e_f32)
+    opt.step()
+    torch.cuda.synchronize()
+    assert abs(opt.last_grad_norm() - gn) <= 3 * abs(r32['grad_norm'] - gn) + 1e-4 * gn
+    sdm = m.state_dict()
+    for k in ('head.0.weight', 'extras.3.conv.3.weight', 'base.17.conv.2.weight', 'base.2.conv.0.0.weight', 'base.0.0.weight'):
+        e_cuda, e_f32 = rel(sdm[k], s64[k]), rel(s32[k], s64[k])
+        assert e_cuda <= 3.0 * e_f32 + 1e-6, (k, e_cuda, e_f32)
+
+
+def test_state_dict_roundtrip_and_checkpoint_keys(tmp_path):
+    sd = synth.synth_state_dict(okrn.krn_shapes(), 11)
+    m = _model(sd)
+    sd2 = m.state_dict()
+    assert list(sd2.keys()) == list(sd.keys())
+    assert all(torch.equal(sd2[k].cpu(), sd[k]) and sd2[k].shape == sd[k].shape for k in sd)
+    from speedplusbaseline_b200.utils import save_checkpoint, load_checkpoint
+    from speedplusbaseline_b200.optim import FusedAdamW
+    opt = FusedAdamW(m._store, m.parameters(), clip_mode=1)
+    save_checkpoint({'epoch': 3, 'model': 'krn', 'state_dict': m.state_dict(), 'best_score': 3, 'optimizer': opt.state_dict()},
+                    True, str(tmp_path))
+    m2 = _model(synth.synth_state_dict(okrn.krn_shapes(), 12))
+    opt2 = FusedAdamW(m2._store, m2.parameters(), clip_mode=1)
+    ep, best = load_checkpoint(str(tmp_path / 'checkpoint.pth.tar'), m2, opt2, torch.device('cuda:0'))
+    assert ep == 3 and all(torch.equal(m2.state_dict()[k].cpu(), sd[k]) for k in sd)
+    best_sd = torch.load(str(tmp_path / 'model_best.pth.tar'), map_location='cpu')
+    assert list(best_sd.keys()) == list(sd.keys())
+
+
+def test_graph_replay_equals_eager_steps():
+    from speedplusbaseline_b200.optim import FusedAdamW
+    from speedplusbaseline_b200.core.trainer import KRNTrainStep
+    sd = synth.synth_state_dict(okrn.krn_shapes(), 2021)
+    out = []
+    for use_graph in (False, True):
+        m = _model(sd).train()
+        opt = FusedAdamW(m._store, m.parameters(), lr=1e-3, weight_decay=0.01, clip_mode=1)
+        stp = KRNTrainStep(m, opt, use_graph=use_graph)
+        losses = []
+        for i in range(3):
+            x, y = synth.synth_images(4, seed=i).cuda(), synth.synth_keypoints(4, seed=i).cuda()
+            losses.append(float(stp.step(x, y)[0]))
+        out.append((losses, m.state_dict()))
+    (l0, s0), (l1, s1) = out
+    assert l0[0] == pytest.approx(l1[0], rel=1e-5)
+    assert int(s1['base.0.1.num_batches_tracked']) == 3
+    # steps 2,3 depend on chaotic fp32 dynamics; the first step must agree tightly, later ones loosely
+    assert l0[1] == pytest.approx(l1[1], rel=5e-2)
+    assert rel(s1['base.0.1.running_mean'], s0['base.0.1.running_mean']) < 1e-3
+
+
+def test_reference_style_loop_with_torch_clip(tmp_path):
+    """The reference's own loop body (trainer.py:78-98) runs unmodified on the module: loss.backward(),
+    torch clip_grad_norm_ on model.parameters(), optimizer.step()."""
+    from torch.nn.utils import clip_grad_norm_
+    from speedplusbaseline_b200.optim import FusedAdamW
+    sd = synth.synth_state_dict(okrn.krn_shapes(), 2021)
+    x, y = synth.synth_images(4), synth.synth_keypoints(4)
+    r32, s32 = _oracle_step(sd, x, y, torch.float32)
+    r64, s64 = _oracle_step(sd, x, y, torch.float64)
+    m = _model(sd).train()
+    opt = FusedAdamW(m._store, m.parameters(), lr=1e-3, weight_decay=0.01, clip_mode=0)
+    loss, summary = m(x.cuda(), y.cuda())
+    opt.zero_grad(set_to_none=True)
+    loss.backward()
+    total = clip_grad_norm_(m.parameters(), 1.0)
+    opt.step()
+    assert float(total) == pytest.approx(r64['grad_norm'], rel=5e-3)
+    # the first Adam update is ~lr*sign(g): elements whose tiny gradient flips sign dominate the error,
+    # for torch fp32 exactly as for the CUDA path -- compare both against float64
+    for k in ('head.0.weight', 'head.0.bias', 'extras.0.conv.3.weight'):
+        e_cuda, e_f32 = rel(m.state_dict()[k], s64[k]), rel(s32[k], s64[k])
+        assert e_cuda <= 3.0 * e_f32 + 1e-6, (k, e_cuda, e_f32)
