@@ -103,6 +103,12 @@ int b200sp_version(void);
 /* number of kernel launches issued through this library since load (the bench's gpu_launches) */
 int64_t b200sp_launch_count(void);
 
+/* tcgen05 plumbing self-test (tc_probe.cu): D[128,N] = A * B^T on one CTA with operands staged in the
+ * library's swizzled shared-memory formats.  mode 0 tf32, 1 3xTF32, 2 bf16; *_major 0: operand given
+ * as [MN][Ktot] (reduction contiguous), 1: as [Ktot][MN].  Ktot = nkb * (32 fp32 | 64 bf16). */
+int b200sp_tc_probe(const void *A, const void *B, float *D, int N, int nkb, int mode,
+                    int a_major, int b_major, int variant, void *stream);
+
 /* ---- convolutions -------------------------------------------------------- */
 /* 3x3 stride-2 pad-1 stem, 3 -> Cout(32), NCHW float input (what the loader yields),
  * NHWC output.  torchvision mobilenetv2.py:126 via park2019.py:107-108. */

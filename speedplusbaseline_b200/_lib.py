@@ -53,6 +53,7 @@ PVT, PBF, PBB = C.POINTER(VTensor), C.POINTER(BnFwd), C.POINTER(BnBwd)
 _SIGS = {
     'b200sp_version': ([], i32),
     'b200sp_launch_count': ([], i64),
+    'b200sp_tc_probe': ([vp, vp, vp, i32, i32, i32, i32, i32, i32, vp], i32),
     'b200sp_stem_fwd': ([vp, vp, vp, PBF, i32, i32, i32, i32, vp], i32),
     'b200sp_stem_wgrad': ([vp, PVT, vp, i32, i32, i32, i32, vp], i32),
     'b200sp_pw_fwd': ([PVT, vp, vp, i32, vp, PBF, i32, i32, i32, i32, vp], i32),
