@@ -1,0 +1,735 @@
+// tcgemm.cu -- persistent, warp-specialised tcgen05 GEMM for the 1x1-convolution / FC family
+// (forward, dgrad, wgrad) with the BatchNorm/activation transforms fused on BOTH sides:
+//
+//   producers (8 warps) : cp.async raw 16-byte pieces of the A and B operands into thread-private
+//                         staging slots (deep prefetch, no register staging), then apply the
+//                         virtual-tensor transform (BN affine + activation, or the folded BatchNorm
+//                         backward dy = cA*g + cB*y + cC), split fp32 into (tf32 hi, lo) or round to
+//                         bf16, and store into the 128B-swizzled UMMA operand tiles;
+//   MMA warp (1 thread) : tcgen05.mma kind::tf32 (x3: lo*hi + hi*lo + hi*hi, fp32-grade accuracy) or
+//                         kind::f16 (bf16) with the 128 x BN fp32 accumulator in TMEM, double-buffered
+//                         so the epilogue of tile i overlaps the main loop of tile i+1;
+//   epilogue (4 warps)  : tcgen05.ld -> per-warp smem transpose -> coalesced global phase doing
+//                         bias/activation (fwd), skip-add + activation-derivative mask (dgrad) or
+//                         fp32 red.add (wgrad), plus the per-channel BatchNorm reductions
+//                         (sum, sumsq | sum g, sum g*xhat) accumulated per CTA and flushed with one
+//                         double atomic per channel; the last CTA finalises the statistics.
+//
+// Operands are consumed in their natural row-major layout: K-major when the reduction dimension is
+// contiguous (fwd A/B, dgrad A), MN-major otherwise (dgrad B = W, wgrad A = dY and B = X), so no
+// transposed weight copies exist anywhere.
+#include <cuda_bf16.h>
+#include "tcgemm.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int EPI_T = 256, MMA_T = 32, PROD_T = 256;
+constexpr int EPI_W = EPI_T / 32;               // 8 epilogue warps: warp w reads TMEM lane quarter w%4, column chunks of parity w/4
+constexpr int MMA_WARP = EPI_W;
+constexpr int NT = EPI_T + MMA_T + PROD_T;     // 544 threads: warps 0-7 epilogue, 8 MMA, 9-16 producers
+constexpr int BM = 128;
+constexpr int STG_LD = 36;                      // floats per epilogue staging row (32 + pad, 16B aligned)
+constexpr int MAX_OP = 4, MAX_RAW = 4;
+
+template <typename T> struct ET;
+template <> struct ET<float> { static constexpr int ES = 4, KE = 32, EPV = 4, NM = 2; static constexpr bool TF32 = true; };
+template <> struct ET<bf16>  { static constexpr int ES = 2, KE = 64, EPV = 8, NM = 1; static constexpr bool TF32 = false; };
+
+struct TcgArgs {
+    b200sp_vtensor a, b;
+    int P, Q, R, lda, ldb;
+    int BN, numPt, numQt, splits, kb_per_split, nkb;
+    int n_op, n_raw;
+    int nb_pieces, nb_slots;         // B pieces per k-block; per-thread B slots = ceil(nb_pieces / PROD_T)
+    int a_dy;
+    int b_res;                       // B (weights) converted once per CTA and kept resident (numQt == 1, fits)
+    int ac_last, nks_last;           // K-major operands: active 16-byte chunks / UMMA k-steps of the LAST k-block
+    uint32_t off_bres;
+    uint32_t a_op_bytes, b_op_bytes; // bytes of ONE math copy (hi or lo) of each operand tile
+    uint32_t op_stage_bytes, raw_stage_bytes;
+    uint32_t off_raw, off_stg, off_stat, off_bar;   // dynamic smem carve-up (from the 1024-aligned base)
+    uint32_t tmem_cols;
+    void* out;
+    const float* bias;
+    int out_act, has_bnf;
+    b200sp_bnfwd bnf;
+    const void* skip;
+    float scale_out;
+    int has_bnb;
+    b200sp_bnbwd bnb;
+    double count;
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// bounded spin: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!tc::mbar_try_wait_hint(bar, parity, 20000u)) {      // hardware-suspended wait (no issue slots burnt)
+        if (++spins > (1u << 22)) __trap();
+    }
+}
+
+// ---- work decomposition ---------------------------------------------------------------------------
+struct Item {
+    int p0, q0, kb0, kb1;
+};
+__device__ __forceinline__ Item get_item(const TcgArgs& g, int it) {
+    Item w;
+    const int qt = it % g.numQt;
+    const int t2 = it / g.numQt;
+    const int pt = t2 % g.numPt, sp = t2 / g.numPt;
+    w.p0 = pt * BM;
+    w.q0 = qt * g.BN;
+    w.kb0 = sp * g.kb_per_split;
+    w.kb1 = min(g.nkb, w.kb0 + g.kb_per_split);
+    return w;
+}
+// flattened (item, k-block) iterator over this CTA's work
+struct KIter {
+    int it, total, stride;
+    Item w;
+    int kb;
+    __device__ __forceinline__ void init(const TcgArgs& g, int first, int total_, int stride_) {
+        it = first; total = total_; stride = stride_;
+        if (it < total) { w = get_item(g, it); kb = w.kb0; }
+    }
+    __device__ __forceinline__ bool valid() const { return it < total; }
+    __device__ __forceinline__ void next(const TcgArgs& g) {
+        if (++kb >= w.kb1) {
+            it += stride;
+            if (it < total) { w = get_item(g, it); kb = w.kb0; }
+        }
+    }
+};
+
+// ---- shared-memory / conversion helpers -----------------------------------------------------------
+__device__ __forceinline__ float4 lds4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts4(uint32_t a, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t u) {
+    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+}
+__device__ __forceinline__ uint32_t f2_to_bf2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ---- per-channel transform of a virtual tensor, mode fixed at compile time --------------------------
+enum { XM_PLAIN = 0, XM_BNACT = 1, XM_DY = 2 };
+struct XfP { float4 a, b, c; };             // BNACT: scale, shift      DY: cA, cB, cC   (4 channels)
+template <int MODE>
+__device__ __forceinline__ void xf_load(const b200sp_vtensor& t, int ch, XfP& p) {
+    if (MODE != XM_PLAIN) { p.a = ldg4(t.p0 + ch); p.b = ldg4(t.p1 + ch); }
+    if (MODE == XM_DY) p.c = ldg4(t.p2 + ch);
+}
+template <int MODE>
+__device__ __forceinline__ float4 xf_apply(float4 x, float4 x2, const XfP& p, ActP act) {
+    if (MODE == XM_PLAIN) return x;
+    if (MODE == XM_BNACT)
+        return make_float4(act_fwd(fmaf(x.x, p.a.x, p.b.x), act), act_fwd(fmaf(x.y, p.a.y, p.b.y), act),
+                           act_fwd(fmaf(x.z, p.a.z, p.b.z), act), act_fwd(fmaf(x.w, p.a.w, p.b.w), act));
+    return make_float4(fmaf(p.a.x, x.x, fmaf(p.b.x, x2.x, p.c.x)), fmaf(p.a.y, x.y, fmaf(p.b.y, x2.y, p.c.y)),
+                       fmaf(p.a.z, x.z, fmaf(p.b.z, x2.z, p.c.z)), fmaf(p.a.w, x.w, fmaf(p.b.w, x2.w, p.c.w)));
+}
+
+// ---- operand loader: one producer thread's share of an operand tile ---------------------------------
+// The 16-byte pieces of a tile are dealt to the 256 producer threads so that each thread owns a fixed
+// (row, chunk) pattern:   piece i (i = 0..np-1) lives at operand-smem offset soff0 + i*sstep.
+//   K-major : chunk c = pt & (AC-1), rows r0 + i*rstep  (AC = active chunks per row, a power of two: a
+//             partial last k-block only converts what the MMA will read); channel = reduction index,
+//             identical for all of a thread's pieces -> transform parameters are fetched once per k-block.
+//   MN-major: chunk c = pt & 7, reduction row r0 (+32 for odd i with bf16), M/N atom i (i>>1 for bf16);
+//             channel = M/N index, fetched per piece.
+template <typename T, int LAY, int MODE>
+struct OpLoader {
+    using E = ET<T>;
+    b200sp_vtensor vt;
+    const char *x, *x2;
+    ActP act;
+    int ld, mn_ext, R, nkb, ac_last;
+    int pt;
+    // geometry: [0] full k-blocks, [1] the partial last k-block (K-major only)
+    int gc0, gc1, gr00, gr01, grstep0, grstep1;
+    uint32_t gsoff0, gsoff1, gsstep0, gsstep1;
+    __device__ __forceinline__ int gc(int gi) const { return gi ? gc1 : gc0; }
+    __device__ __forceinline__ int gr0(int gi) const { return gi ? gr01 : gr00; }
+    __device__ __forceinline__ int grstep(int gi) const { return gi ? grstep1 : grstep0; }
+    __device__ __forceinline__ uint32_t gsoff(int gi) const { return gi ? gsoff1 : gsoff0; }
+    __device__ __forceinline__ uint32_t gsstep(int gi) const { return gi ? gsstep1 : gsstep0; }
+    int cached_kb;
+    XfP par;
+
+    __device__ __forceinline__ void init(const b200sp_vtensor& t, int ld_, int mn_ext_, int R_, int nkb_, int ac_last_, int pt_) {
+        vt = t; x = reinterpret_cast<const char*>(t.x); x2 = reinterpret_cast<const char*>(t.x2);
+        act = act_params(t.act);
+        ld = ld_; mn_ext = mn_ext_; R = R_; nkb = nkb_; ac_last = ac_last_; pt = pt_;
+        cached_kb = -1;
+        if (LAY == TCG_LAY_KM) {
+            gc0 = pt & 7; gr00 = pt >> 3; grstep0 = PROD_T >> 3;
+            gsoff0 = tc::sw128_off(gr00, gc0); gsstep0 = grstep0 * 128;
+            const int lg = ac_last > 4 ? 3 : (ac_last > 2 ? 2 : 1);
+            gc1 = pt & ((1 << lg) - 1); gr01 = pt >> lg; grstep1 = PROD_T >> lg;
+            gsoff1 = tc::sw128_off(gr01, gc1); gsstep1 = grstep1 * 128;
+        } else {
+            gc0 = gc1 = pt & 7;
+            gr00 = gr01 = pt >> 3;
+            grstep0 = grstep1 = 0;
+            gsoff0 = gsoff1 = E::TF32 ? tc::sw128b32_off(pt >> 3, pt & 7) : tc::sw128_off(pt >> 3, pt & 7);
+            gsstep0 = gsstep1 = 4096;
+        }
+    }
+    // source of piece i of k-block kb for the tile starting at M/N index mn0
+    __device__ __forceinline__ bool src(int kb, int mn0, int i, int gi, size_t& boff, int& ch) const {
+        int mn, red;
+        if (LAY == TCG_LAY_KM) {
+            mn = mn0 + gr0(gi) + i * grstep(gi);
+            red = kb * E::KE + gc(gi) * E::EPV;
+            ch = red;
+            boff = ((size_t)mn * ld + red) * E::ES;
+            return mn < mn_ext && red < R && (gi == 0 || gc(gi) < ac_last);
+        }
+        if (E::TF32) { red = kb * E::KE + gr0(0); mn = mn0 + i * 32 + gc(0) * 4; }
+        else         { red = kb * E::KE + gr0(0) + 32 * (i & 1); mn = mn0 + (i >> 1) * 64 + gc(0) * 8; }
+        ch = mn;
+        boff = ((size_t)red * ld + mn) * E::ES;
+        return mn < mn_ext && red < R;
+    }
+    __device__ __forceinline__ int geom(int kb) const { return (LAY == TCG_LAY_KM && kb == nkb - 1 && ac_last != 8) ? 1 : 0; }
+    // number of pieces this thread owns for a tile `ext` M/N elements wide
+    __device__ __forceinline__ int count(int gi, int ext) const {
+        if (LAY == TCG_LAY_KM) {
+            if (gi == 1 && gc(1) >= ac_last) return 0;
+            const int rem = ext - gr0(gi);
+            return rem <= 0 ? 0 : (rem + grstep(gi) - 1) / grstep(gi);
+        }
+        const int atoms = (ext * E::ES + 127) / 128;
+        return E::TF32 ? atoms : 2 * atoms;
+    }
+    // cp.async this thread's raw pieces of k-block kb into its private slots (slot i at raw + i*PROD_T*16)
+    template <int NP>
+    __device__ __forceinline__ void issue(int kb, int mn0, int np, uint32_t raw, uint32_t raw2) const {
+        const int gi = geom(kb);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            if (i < np) {
+                size_t boff; int ch;
+                const bool ok = src(kb, mn0, i, gi, boff, ch);
+                cp_async16(raw + i * (PROD_T * 16), x + (ok ? boff : 0), ok);
+                if (MODE == XM_DY) cp_async16(raw2 + i * (PROD_T * 16), x2 + (ok ? boff : 0), ok);
+            }
+        }
+    }
+    // transform the raw pieces and store them into the operand tile (hi [, lo])
+    template <int NP>
+    __device__ __forceinline__ void convert(int kb, int mn0, int np, uint32_t raw, uint32_t raw2, uint32_t op_hi, uint32_t op_lo) {
+        const int gi = geom(kb);
+        if (LAY == TCG_LAY_KM && MODE != XM_PLAIN && kb != cached_kb) {
+            const int ch = kb * E::KE + gc(gi) * E::EPV;
+            if (ch + E::EPV <= R) {
+                xf_load<MODE>(vt, ch, par);
+                if (!E::TF32) xf_load<MODE>(vt, ch + 4, par2);
+            }
+            cached_kb = kb;
+        }
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            if (i < np) {
+                size_t boff; int ch;
+                const bool ok = src(kb, mn0, i, gi, boff, ch);
+                const uint32_t so = gsoff(gi) + i * gsstep(gi);
+                float4 r = lds4(raw + i * (PROD_T * 16)), r2 = f4zero();
+                if (MODE == XM_DY) r2 = lds4(raw2 + i * (PROD_T * 16));
+                if (LAY == TCG_LAY_MM && MODE != XM_PLAIN && ok) {
+                    xf_load<MODE>(vt, ch, par);
+                    if (!E::TF32) xf_load<MODE>(vt, ch + 4, par2);
+                }
+                if (E::TF32) {
+                    float4 v = xf_apply<MODE>(r, r2, par, act);
+                    if (!ok) v = f4zero();
+                    float4 h, l;
+                    tc::split_tf32(v.x, h.x, l.x); tc::split_tf32(v.y, h.y, l.y);
+                    tc::split_tf32(v.z, h.z, l.z); tc::split_tf32(v.w, h.w, l.w);
+                    sts4(op_hi + so, h);
+                    sts4(op_lo + so, l);
+                } else {
+                    float4 o = r;
+                    if (MODE != XM_PLAIN) {
+                        const uint32_t* u = reinterpret_cast<const uint32_t*>(&r);
+                        const uint32_t* u2 = reinterpret_cast<const uint32_t*>(&r2);
+                        const float2 a0 = bf2_to_f2(u[0]), a1 = bf2_to_f2(u[1]), a2 = bf2_to_f2(u[2]), a3 = bf2_to_f2(u[3]);
+                        const float2 b0 = bf2_to_f2(u2[0]), b1 = bf2_to_f2(u2[1]), b2 = bf2_to_f2(u2[2]), b3 = bf2_to_f2(u2[3]);
+                        const float4 lo4 = xf_apply<MODE>(make_float4(a0.x, a0.y, a1.x, a1.y), make_float4(b0.x, b0.y, b1.x, b1.y), par, act);
+                        const float4 hi4 = xf_apply<MODE>(make_float4(a2.x, a2.y, a3.x, a3.y), make_float4(b2.x, b2.y, b3.x, b3.y), par2, act);
+                        uint32_t* w = reinterpret_cast<uint32_t*>(&o);
+                        w[0] = f2_to_bf2(lo4.x, lo4.y); w[1] = f2_to_bf2(lo4.z, lo4.w);
+                        w[2] = f2_to_bf2(hi4.x, hi4.y); w[3] = f2_to_bf2(hi4.z, hi4.w);
+                    }
+                    if (!ok) o = f4zero();
+                    sts4(op_hi + so, o);
+                }
+            }
+        }
+    }
+    XfP par2;
+};
+
+// =====================================================================================================
+template <typename T, int ALAY, int BLAY, int EPI, int AMODE, int BMODE>
+__global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
+    using E = ET<T>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t s_base = tc::smem_u32(smem);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.off_bar);
+    uint64_t* full = bars;                    // [MAX_OP]  producers -> MMA
+    uint64_t* empty = bars + MAX_OP;          // [MAX_OP]  MMA -> producers
+    uint64_t* tfull = bars + 2 * MAX_OP;      // [2]       MMA -> epilogue
+    uint64_t* tempty = bars + 2 * MAX_OP + 2; // [2]       epilogue -> MMA
+    uint64_t* bfull = bars + 2 * MAX_OP + 4;  // [1]       producers -> MMA: resident B converted
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_OP + 5);
+    int* s_flag = reinterpret_cast<int*>(tmem_slot + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int total = g.numPt * g.numQt * g.splits;
+
+    if (tid == 0) {
+        for (int i = 0; i < MAX_OP; ++i) { tc::mbar_init(&full[i], PROD_T / 32); tc::mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], EPI_W); }
+        tc::mbar_init(bfull, PROD_T / 32);
+        tc::mbar_fence_init();
+    }
+    if (warp == MMA_WARP) { tc::tmem_alloc(tmem_slot, g.tmem_cols); tc::tmem_relinquish(); }
+    if (tid < EPI_T) {          // zero the per-warp statistic accumulators
+        float* st = reinterpret_cast<float*>(smem + g.off_stat);
+        for (int i = tid; i < EPI_W * 2 * g.BN; i += EPI_T) st[i] = 0.f;
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // operand tile offsets inside one ring stage (A only when B is resident)
+    const uint32_t b_in_stage = E::NM * g.a_op_bytes;
+
+    if (warp > MMA_WARP) {
+        // ======================================= PRODUCERS =======================================
+        const int pt = tid - (EPI_T + MMA_T);
+        constexpr int NPB = E::TF32 ? 4 : 8;
+        OpLoader<T, ALAY, AMODE> LA;
+        OpLoader<T, BLAY, BMODE> LB;
+        LA.init(g.a, g.lda, g.P, g.R, g.nkb, g.ac_last, pt);
+        LB.init(g.b, g.ldb, g.Q, g.R, g.nkb, g.ac_last, pt);
+        const uint32_t raw0 = s_base + g.off_raw + pt * 16;
+        constexpr int slotA2 = 4, slotB = AMODE == XM_DY ? 8 : 4;
+        if (g.b_res) {
+            // weights: convert every k-block once, keep them resident for all of this CTA's tiles
+            for (int kb = 0; kb < g.nkb; ++kb) {
+                const int np = LB.count(LB.geom(kb), g.BN);
+                const uint32_t b_hi = s_base + g.off_bres + kb * (E::NM * g.b_op_bytes), b_lo = b_hi + g.b_op_bytes;
+                LB.template issue<NPB>(kb, 0, np, raw0, 0);
+                cp_async_commit();
+                cp_async_wait<0>();
+                LB.template convert<NPB>(kb, 0, np, raw0, 0, b_hi, b_lo);
+            }
+            tc::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(bfull);
+        }
+        KIter fetch, cons;
+        fetch.init(g, blockIdx.x, total, gridDim.x);
+        cons.init(g, blockIdx.x, total, gridDim.x);
+
+        auto issue = [&](const KIter& k, int rs) {
+            const uint32_t rbase = raw0 + rs * g.raw_stage_bytes;
+            LA.template issue<4>(k.kb, k.w.p0, LA.count(LA.geom(k.kb), BM), rbase, rbase + slotA2 * (PROD_T * 16));
+            if (!g.b_res) LB.template issue<NPB>(k.kb, k.w.q0, LB.count(LB.geom(k.kb), g.BN), rbase + slotB * (PROD_T * 16), 0);
+        };
+
+        for (int d = 0; d < g.n_raw; ++d) {
+            if (fetch.valid()) { issue(fetch, d); fetch.next(g); }
+            cp_async_commit();
+        }
+        int n = 0;
+        while (cons.valid()) {
+            if (g.n_raw == 4) cp_async_wait<3>(); else if (g.n_raw == 3) cp_async_wait<2>(); else cp_async_wait<1>();
+            const int rs = n % g.n_raw, os = n % g.n_op;
+            const uint32_t par = ((n / g.n_op) & 1) ^ 1;
+            mbar_wait_guard(&empty[os], par);
+            const uint32_t rbase = raw0 + rs * g.raw_stage_bytes;
+            const uint32_t a_hi = s_base + os * g.op_stage_bytes, a_lo = a_hi + g.a_op_bytes;
+            const uint32_t b_hi = a_hi + b_in_stage, b_lo = b_hi + g.b_op_bytes;
+            LA.template convert<4>(cons.kb, cons.w.p0, LA.count(LA.geom(cons.kb), BM), rbase, rbase + slotA2 * (PROD_T * 16), a_hi, a_lo);
+            if (!g.b_res)
+                LB.template convert<NPB>(cons.kb, cons.w.q0, LB.count(LB.geom(cons.kb), g.BN), rbase + slotB * (PROD_T * 16), 0, b_hi, b_lo);
+            tc::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&full[os]);
+            // refill the raw slot just consumed with the k-block n_raw ahead
+            if (fetch.valid()) { issue(fetch, rs); fetch.next(g); }
+            cp_async_commit();
+            cons.next(g);
+            ++n;
+        }
+        cp_async_wait<0>();
+    } else if (warp == MMA_WARP) {
+        // ======================================= MMA ISSUER ======================================
+        const uint32_t idesc = tc::make_idesc(E::TF32 ? tc::FMT_TF32 : tc::FMT_BF16, ALAY == TCG_LAY_MM, BLAY == TCG_LAY_MM, BM, g.BN);
+        // per-k-step start-address advance (bytes) and LBO / SBO / layout of each operand
+        constexpr uint32_t KSTEP_KM = 32, KSTEP_MM = (E::TF32 ? 8 : 16) * 128;
+        constexpr uint32_t LBO_MM = E::KE * 128, SBO_MM = E::TF32 ? 512 : 1024;
+        constexpr uint32_t LT_MM = E::TF32 ? tc::SWZ_128B_BASE32B : tc::SWZ_128B;
+        auto adesc = [&](uint32_t base, int ks) {
+            return ALAY == TCG_LAY_KM ? tc::smem_desc(base + ks * KSTEP_KM, 0, 1024, tc::SWZ_128B)
+                                      : tc::smem_desc(base + ks * KSTEP_MM, LBO_MM, SBO_MM, LT_MM);
+        };
+        auto bdesc = [&](uint32_t base, int ks) {
+            return BLAY == TCG_LAY_KM ? tc::smem_desc(base + ks * KSTEP_KM, 0, 1024, tc::SWZ_128B)
+                                      : tc::smem_desc(base + ks * KSTEP_MM, LBO_MM, SBO_MM, LT_MM);
+        };
+        if (g.b_res) { mbar_wait_guard(bfull, 0); tc::tc_fence_after(); }
+        int n = 0, ni = 0;
+        for (int it = blockIdx.x; it < total; it += gridDim.x, ++ni) {
+            const Item w = get_item(g, it);
+            const int acc = ni & 1;
+            mbar_wait_guard(&tempty[acc], ((ni >> 1) & 1) ^ 1);
+            tc::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * g.BN;
+            for (int kb = w.kb0; kb < w.kb1; ++kb, ++n) {
+                const int os = n % g.n_op;
+                mbar_wait_guard(&full[os], (n / g.n_op) & 1);
+                tc::tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_hi = s_base + os * g.op_stage_bytes, a_lo = a_hi + g.a_op_bytes;
+                    const uint32_t b_hi = g.b_res ? s_base + g.off_bres + kb * (E::NM * g.b_op_bytes) : a_hi + b_in_stage;
+                    const uint32_t b_lo = b_hi + g.b_op_bytes;
+                    // a K-major operand only holds the active chunks of a partial last k-block: never read beyond them
+                    const int nks = ((ALAY == TCG_LAY_KM || BLAY == TCG_LAY_KM) && kb == g.nkb - 1) ? g.nks_last : 4;
+                    for (int ks = 0; ks < nks; ++ks) {
+                        const uint32_t accum = (kb > w.kb0 || ks > 0) ? 1u : 0u;
+                        if (E::TF32) {
+                            tc::umma<true>(d_tmem, adesc(a_lo, ks), bdesc(b_hi, ks), idesc, accum);
+                            tc::umma<true>(d_tmem, adesc(a_hi, ks), bdesc(b_lo, ks), idesc, 1u);
+                            tc::umma<true>(d_tmem, adesc(a_hi, ks), bdesc(b_hi, ks), idesc, 1u);
+                        } else {
+                            tc::umma<false>(d_tmem, adesc(a_hi, ks), bdesc(b_hi, ks), idesc, accum);
+                        }
+                    }
+                    tc::umma_commit(&empty[os]);
+                    if (kb == w.kb1 - 1) tc::umma_commit(&tfull[acc]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ======================================= EPILOGUE ========================================
+        const int lq = warp & 3, half = warp >> 2;      // TMEM lane quarter, column-chunk parity
+        float* stg = reinterpret_cast<float*>(smem + g.off_stg) + warp * (32 * STG_LD);
+        const uint32_t stg_u = tc::smem_u32(stg);
+        float* stat_all = reinterpret_cast<float*>(smem + g.off_stat);      // [EPI_W][2][BN]
+        float* stat = stat_all + warp * (2 * g.BN);
+        const bool do_stats = (EPI == TCG_EPI_FWD && g.has_bnf) || (EPI == TCG_EPI_DGRAD && g.has_bnb && g.bnb.s1 != nullptr);
+        const bool plain_out = EPI == TCG_EPI_FWD && g.bias == nullptr && g.out_act == B200SP_ACT_NONE;
+        const int cq = lane & 7, rs = lane >> 3;
+        const ActP oact = act_params(EPI == TCG_EPI_FWD ? g.out_act : g.bnb.act);
+        T* outT = reinterpret_cast<T*>(g.out);
+        float* outF = reinterpret_cast<float*>(g.out);
+        const int nchunks = (g.BN + 31) >> 5;
+        int last_chunk = -1;                            // last chunk this warp reads from TMEM
+        for (int c = half; c < nchunks; c += 2) last_chunk = c;
+        int ni = 0;
+        int cur_q0 = -1;
+        auto flush = [&](int q0) {
+            epi_bar();
+            for (int c = tid; c < g.BN; c += EPI_T) {
+                double a = 0.0, b = 0.0;
+#pragma unroll
+                for (int w = 0; w < EPI_W; ++w) {
+                    a += (double)stat_all[w * 2 * g.BN + c];
+                    b += (double)stat_all[w * 2 * g.BN + g.BN + c];
+                    stat_all[w * 2 * g.BN + c] = 0.f;
+                    stat_all[w * 2 * g.BN + g.BN + c] = 0.f;
+                }
+                if (q0 + c < g.Q) {
+                    if (EPI == TCG_EPI_FWD) { atomicAdd(g.bnf.sum + q0 + c, a); atomicAdd(g.bnf.sumsq + q0 + c, b); }
+                    else                    { atomicAdd(g.bnb.s1 + q0 + c, a);  atomicAdd(g.bnb.s2 + q0 + c, b); }
+                }
+            }
+            epi_bar();
+        };
+        for (int it = blockIdx.x; it < total; it += gridDim.x, ++ni) {
+            const Item w = get_item(g, it);
+            const int acc = ni & 1;
+            if (do_stats && cur_q0 >= 0 && cur_q0 != w.q0) flush(cur_q0);
+            cur_q0 = w.q0;
+            mbar_wait_guard(&tfull[acc], (ni >> 1) & 1);
+            tc::tc_fence_after();
+            const uint32_t t_row = tmem_base + acc * g.BN + ((uint32_t)(lq * 32) << 16);
+            if (last_chunk < 0) {                        // nothing to read for this warp: release immediately
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&tempty[acc]);
+            }
+            for (int ci = half; ci < nchunks; ci += 2) {
+                const int c0 = ci * 32;
+                const int ncol = min(32, g.BN - c0);
+                uint32_t r[32];
+                if (ncol == 32) {
+                    tc::tmem_ld32(t_row + c0, r);
+                } else {
+                    uint32_t r16[16];
+                    tc::tmem_ld16(t_row + c0, r16);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { r[i] = r16[i]; r[16 + i] = 0u; }
+                }
+                tc::tmem_ld_wait();
+                if (ci == last_chunk) {         // accumulator drained by this warp: hand TMEM back to the MMA warp
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&tempty[acc]);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    sts4(stg_u + (lane * STG_LD + 4 * j) * 4,
+                         make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+                __syncwarp();
+                // ---- coalesced phase: lane = (row sub-index rs, column quad cq) ----
+                const int col = w.q0 + c0 + 4 * cq;
+                const bool cok = 4 * cq < ncol && col < g.Q;
+                float4 bias4 = f4zero(), sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sh4 = f4zero(), mu4 = f4zero(), rs4 = f4zero();
+                if (cok) {
+                    if (EPI == TCG_EPI_FWD && g.bias) bias4 = ldg4(g.bias + col);
+                    if (EPI == TCG_EPI_DGRAD && g.has_bnb) {
+                        if (g.bnb.scale) { sc4 = ldg4(g.bnb.scale + col); sh4 = ldg4(g.bnb.shift + col); }
+                        if (g.bnb.s1) { mu4 = ldg4(g.bnb.mean + col); rs4 = ldg4(g.bnb.rstd + col); }
+                    }
+                }
+                float4 ls = f4zero(), lq4 = f4zero();
+                const int row_base = w.p0 + lq * 32 + rs;
+#pragma unroll
+                for (int ps = 0; ps < 8; ++ps) {
+                    const int trow = ps * 4 + rs;
+                    const int row = row_base + ps * 4;
+                    if (!(cok && row < g.P)) continue;
+                    float4 v = lds4(stg_u + (trow * STG_LD + 4 * cq) * 4);
+                    const size_t off = (size_t)row * g.Q + col;
+                    if (EPI == TCG_EPI_FWD) {
+                        if (!plain_out) {
+                            v.x = act_fwd(v.x + bias4.x, oact); v.y = act_fwd(v.y + bias4.y, oact);
+                            v.z = act_fwd(v.z + bias4.z, oact); v.w = act_fwd(v.w + bias4.w, oact);
+                        }
+                        Vec4<T>::st(outT + off, v);
+                        if (!E::TF32) {      // statistics of the value as stored (bf16-rounded)
+                            v.x = __bfloat162float(__float2bfloat16_rn(v.x)); v.y = __bfloat162float(__float2bfloat16_rn(v.y));
+                            v.z = __bfloat162float(__float2bfloat16_rn(v.z)); v.w = __bfloat162float(__float2bfloat16_rn(v.w));
+                        }
+                        ls.x += v.x; ls.y += v.y; ls.z += v.z; ls.w += v.w;
+                        lq4.x = fmaf(v.x, v.x, lq4.x); lq4.y = fmaf(v.y, v.y, lq4.y); lq4.z = fmaf(v.z, v.z, lq4.z); lq4.w = fmaf(v.w, v.w, lq4.w);
+                    } else if (EPI == TCG_EPI_DGRAD) {
+                        v.x *= g.scale_out; v.y *= g.scale_out; v.z *= g.scale_out; v.w *= g.scale_out;
+                        if (g.skip) {
+                            const float4 s = Vec4<T>::ld(reinterpret_cast<const T*>(g.skip) + off);
+                            v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
+                        }
+                        if (g.has_bnb) {
+                            const float4 y = Vec4<T>::ld(reinterpret_cast<const T*>(g.bnb.y) + off);
+                            v.x *= act_bwd(fmaf(y.x, sc4.x, sh4.x), oact); v.y *= act_bwd(fmaf(y.y, sc4.y, sh4.y), oact);
+                            v.z *= act_bwd(fmaf(y.z, sc4.z, sh4.z), oact); v.w *= act_bwd(fmaf(y.w, sc4.w, sh4.w), oact);
+                            ls.x += v.x; ls.y += v.y; ls.z += v.z; ls.w += v.w;
+                            lq4.x = fmaf(v.x, (y.x - mu4.x) * rs4.x, lq4.x); lq4.y = fmaf(v.y, (y.y - mu4.y) * rs4.y, lq4.y);
+                            lq4.z = fmaf(v.z, (y.z - mu4.z) * rs4.z, lq4.z); lq4.w = fmaf(v.w, (y.w - mu4.w) * rs4.w, lq4.w);
+                        }
+                        Vec4<T>::st(outT + off, v);
+                    } else {
+                        atomicAdd(outF + off, v.x); atomicAdd(outF + off + 1, v.y);
+                        atomicAdd(outF + off + 2, v.z); atomicAdd(outF + off + 3, v.w);
+                    }
+                }
+                if (do_stats) {
+#pragma unroll
+                    for (int o = 8; o < 32; o <<= 1) {
+                        ls.x += __shfl_xor_sync(0xffffffffu, ls.x, o); ls.y += __shfl_xor_sync(0xffffffffu, ls.y, o);
+                        ls.z += __shfl_xor_sync(0xffffffffu, ls.z, o); ls.w += __shfl_xor_sync(0xffffffffu, ls.w, o);
+                        lq4.x += __shfl_xor_sync(0xffffffffu, lq4.x, o); lq4.y += __shfl_xor_sync(0xffffffffu, lq4.y, o);
+                        lq4.z += __shfl_xor_sync(0xffffffffu, lq4.z, o); lq4.w += __shfl_xor_sync(0xffffffffu, lq4.w, o);
+                    }
+                    if (rs == 0 && 4 * cq < ncol) {
+                        float* s0 = stat + c0 + 4 * cq;
+                        float* s1 = stat + g.BN + c0 + 4 * cq;
+                        s0[0] += ls.x; s0[1] += ls.y; s0[2] += ls.z; s0[3] += ls.w;
+                        s1[0] += lq4.x; s1[1] += lq4.y; s1[2] += lq4.z; s1[3] += lq4.w;
+                    }
+                }
+                __syncwarp();      // staging tile is reused by the next column chunk
+            }
+        }
+        if (do_stats) {
+            if (cur_q0 >= 0) flush(cur_q0);
+            // elect the last CTA of the grid: it turns the accumulated sums into scale/shift (fwd) or dy coefficients (bwd)
+            __threadfence();
+            epi_bar();
+            if (tid == 0) {
+                uint32_t* ticket = EPI == TCG_EPI_FWD ? g.bnf.ticket : g.bnb.ticket;
+                const uint32_t t = atomicAdd(ticket, 1u);
+                const int last = (t == gridDim.x - 1);
+                if (last) *ticket = 0u;
+                *s_flag = last;
+            }
+            epi_bar();
+            if (*s_flag) {
+                __threadfence();
+                for (int c = tid; c < g.Q; c += EPI_T) {
+                    if (EPI == TCG_EPI_FWD) bn_fwd_finalize_channel(g.bnf, c, g.count);
+                    else                    bn_bwd_finalize_channel(g.bnb, c, g.count);
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    if (warp == MMA_WARP) tc::tmem_dealloc(tmem_base, g.tmem_cols);
+}
+
+// -------------------------------------------------------------------------------------------------
+constexpr uint32_t SMEM_LIMIT = 227 * 1024;
+constexpr uint32_t BRES_LIMIT = 64 * 1024;
+
+template <typename T, int ALAY, int BLAY, int EPI, int AMODE, int BMODE>
+int launch_cfg(TcgArgs& a, cudaStream_t st) {
+    using E = ET<T>;
+    static bool attr_set = false;
+    auto kern = tcgemm_kernel<T, ALAY, BLAY, EPI, AMODE, BMODE>;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int numPt = ceil_div(a.P, BM);
+    a.nkb = ceil_div(a.R, E::KE);
+    // ---- partial last k-block of K-major operands ----
+    {
+        const int rem = a.R - (a.nkb - 1) * E::KE;             // 1..KE elements
+        const int kstep = 2 * E::EPV;                          // elements per UMMA k-step (32 bytes)
+        a.nks_last = ceil_div(rem, kstep);
+        a.ac_last = 2 * a.nks_last;
+    }
+    // ---- tile width: the widest that fits shared memory; narrower while the grid does not cover the machine ----
+    const int cap0 = E::TF32 ? 128 : 256;
+    bool fits = false;
+    for (int cap = cap0; cap >= 32 && !fits; cap -= (cap > 64 ? 32 : 16)) {
+        int numQt = ceil_div(a.Q, cap);
+        int BN = ceil_div(ceil_div(a.Q, numQt), 16) * 16;
+        if (EPI != TCG_EPI_ATOMIC) {
+            while (numPt * numQt < NUM_SMS && BN > 32) {
+                ++numQt;
+                BN = ceil_div(ceil_div(a.Q, numQt), 16) * 16;
+            }
+        }
+        numQt = ceil_div(a.Q, BN);
+        a.BN = BN; a.numPt = numPt; a.numQt = numQt;
+        a.a_op_bytes = BM * 128;
+        const int atoms_b = ceil_div(BN * E::ES, 128);
+        a.b_op_bytes = BLAY == TCG_LAY_KM ? BN * 128 : atoms_b * E::KE * 128;
+        a.nb_pieces = a.b_op_bytes / 16;
+        a.nb_slots = ceil_div(a.nb_pieces, PROD_T);
+        const uint32_t bres_bytes = (uint32_t)a.nkb * E::NM * a.b_op_bytes;
+        a.b_res = (EPI != TCG_EPI_ATOMIC && numQt == 1 && BMODE == XM_PLAIN && bres_bytes <= BRES_LIMIT) ? 1 : 0;
+        a.op_stage_bytes = E::NM * (a.a_op_bytes + (a.b_res ? 0 : a.b_op_bytes));
+        a.raw_stage_bytes = (4 + (AMODE == XM_DY ? 4 : 0) + (a.b_res ? 0 : a.nb_slots)) * PROD_T * 16;
+        const uint32_t fixed = EPI_W * 32 * STG_LD * 4 + EPI_W * 2 * BN * 4 + 256 + (a.b_res ? bres_bytes : 0);
+        a.n_op = 2;
+        a.n_raw = 0;
+        for (int nr = MAX_RAW; nr >= 2; --nr) {
+            if (a.n_op * a.op_stage_bytes + nr * a.raw_stage_bytes + fixed + 1088 <= SMEM_LIMIT) { a.n_raw = nr; break; }
+        }
+        if (a.n_raw == 0) continue;
+        fits = true;
+        while (a.n_op < MAX_OP && (a.n_op + 1) * a.op_stage_bytes + a.n_raw * a.raw_stage_bytes + fixed + 1088 <= SMEM_LIMIT) ++a.n_op;
+        a.off_bres = a.n_op * a.op_stage_bytes;
+        a.off_raw = a.off_bres + (a.b_res ? bres_bytes : 0);
+        a.off_stg = a.off_raw + a.n_raw * a.raw_stage_bytes;
+        a.off_stat = a.off_stg + EPI_W * 32 * STG_LD * 4;
+        a.off_bar = (a.off_stat + EPI_W * 2 * BN * 4 + 15) & ~15u;
+    }
+    if (!fits) return B200SP_ENOSYS;
+    const int numQt = a.numQt, BN = a.BN;
+    // ---- reduction splits (wgrad only: results are accumulated atomically) ----
+    a.splits = 1;
+    if (EPI == TCG_EPI_ATOMIC) {
+        const int base = numPt * numQt;
+        int s = ceil_div(2 * NUM_SMS, base);
+        const int smax = a.nkb / 4 > 0 ? a.nkb / 4 : 1;
+        if (s > smax) s = smax;
+        if (s < 1) s = 1;
+        a.splits = s;
+    }
+    a.kb_per_split = ceil_div(a.nkb, a.splits);
+    a.splits = ceil_div(a.nkb, a.kb_per_split);
+    const uint32_t smem = a.off_bar + 256 + 1024;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(2 * BN)) cols <<= 1;
+    a.tmem_cols = cols;
+    const int total = numPt * numQt * a.splits;
+    const int grid = total < NUM_SMS ? total : NUM_SMS;
+    kern<<<grid, NT, smem, st>>>(a);
+    B200SP_COUNT_LAUNCH();
+    B200SP_RETURN_LAST();
+}
+
+template <typename T>
+int launch_T(TcgArgs& a, const TcgProblem& p, cudaStream_t st) {
+    const int am = p.a.mode, bm = p.b.mode;
+    if (p.epi == TCG_EPI_FWD && p.a_lay == TCG_LAY_KM && p.b_lay == TCG_LAY_KM && bm == B200SP_VT_PLAIN) {
+        if (am == B200SP_VT_PLAIN) return launch_cfg<T, TCG_LAY_KM, TCG_LAY_KM, TCG_EPI_FWD, XM_PLAIN, XM_PLAIN>(a, st);
+        if (am == B200SP_VT_BNACT) return launch_cfg<T, TCG_LAY_KM, TCG_LAY_KM, TCG_EPI_FWD, XM_BNACT, XM_PLAIN>(a, st);
+    }
+    if (p.epi == TCG_EPI_DGRAD && p.a_lay == TCG_LAY_KM && p.b_lay == TCG_LAY_MM && bm == B200SP_VT_PLAIN) {
+        if (am == B200SP_VT_PLAIN) return launch_cfg<T, TCG_LAY_KM, TCG_LAY_MM, TCG_EPI_DGRAD, XM_PLAIN, XM_PLAIN>(a, st);
+        if (am == B200SP_VT_DY) return launch_cfg<T, TCG_LAY_KM, TCG_LAY_MM, TCG_EPI_DGRAD, XM_DY, XM_PLAIN>(a, st);
+    }
+    if (p.epi == TCG_EPI_ATOMIC && p.a_lay == TCG_LAY_MM && p.b_lay == TCG_LAY_MM) {
+        if (am == B200SP_VT_PLAIN && bm == B200SP_VT_PLAIN) return launch_cfg<T, TCG_LAY_MM, TCG_LAY_MM, TCG_EPI_ATOMIC, XM_PLAIN, XM_PLAIN>(a, st);
+        if (am == B200SP_VT_PLAIN && bm == B200SP_VT_BNACT) return launch_cfg<T, TCG_LAY_MM, TCG_LAY_MM, TCG_EPI_ATOMIC, XM_PLAIN, XM_BNACT>(a, st);
+        if (am == B200SP_VT_DY && bm == B200SP_VT_PLAIN) return launch_cfg<T, TCG_LAY_MM, TCG_LAY_MM, TCG_EPI_ATOMIC, XM_DY, XM_PLAIN>(a, st);
+        if (am == B200SP_VT_DY && bm == B200SP_VT_BNACT) return launch_cfg<T, TCG_LAY_MM, TCG_LAY_MM, TCG_EPI_ATOMIC, XM_DY, XM_BNACT>(a, st);
+    }
+    return B200SP_ENOSYS;
+}
+
+}  // namespace
+
+int tcgemm_launch(const TcgProblem& p, cudaStream_t st) {
+    const int epv = p.dtype == B200SP_F32 ? 4 : 8;
+    // vector-piece granularity: every contiguous extent must be a whole number of 16-byte pieces
+    if (p.Q % 4 || p.lda % epv || p.ldb % epv) return B200SP_ENOSYS;
+    if (p.a_lay == TCG_LAY_KM ? (p.R % epv) : (p.P % epv)) return B200SP_ENOSYS;
+    if (p.b_lay == TCG_LAY_KM ? (p.R % epv) : (p.Q % epv)) return B200SP_ENOSYS;
+    if (p.b.mode == B200SP_VT_DY) return B200SP_ENOSYS;
+    if (((uintptr_t)p.a.x | (uintptr_t)p.b.x | (uintptr_t)p.a.x2 | (uintptr_t)p.out) & 15) return B200SP_ENOSYS;
+    TcgArgs a = {};
+    a.a = p.a; a.b = p.b;
+    a.P = p.P; a.Q = p.Q; a.R = p.R; a.lda = p.lda; a.ldb = p.ldb;
+    a.a_dy = p.a.mode == B200SP_VT_DY;
+    a.out = p.out; a.bias = p.bias; a.out_act = p.out_act;
+    a.has_bnf = p.bnf != nullptr;
+    if (p.bnf) a.bnf = *p.bnf;
+    a.skip = p.skip; a.scale_out = p.scale_out;
+    a.has_bnb = p.bnb != nullptr;
+    if (p.bnb) a.bnb = *p.bnb;
+    a.count = p.count;
+    if (p.dtype == B200SP_F32) return launch_T<float>(a, p, st);
+    if (p.dtype == B200SP_BF16) return launch_T<bf16>(a, p, st);
+    return B200SP_ENOSYS;
+}

@@ -1,0 +1,32 @@
+// tcgemm.cuh -- internal interface between the C-ABI GEMM entry points (gemm.cu) and the
+// tcgen05 kernel (tcgemm.cu).
+#pragma once
+#include "common.cuh"
+
+enum { TCG_LAY_KM = 0, TCG_LAY_MM = 1 };
+enum { TCG_EPI_FWD = 0, TCG_EPI_DGRAD = 1, TCG_EPI_ATOMIC = 2 };
+
+// C[P,Q] = sum_r A(p,r) * B(q,r).  Layout KM: the operand is stored [MN][R] (reduction contiguous),
+// MM: stored [R][MN].  The per-channel transform of a virtual tensor indexes the CONTIGUOUS dimension.
+struct TcgProblem {
+    b200sp_vtensor a, b;
+    int a_lay, b_lay;
+    int P, Q, R;
+    int lda, ldb;
+    int epi;
+    int dtype;                 // B200SP_F32 (3xTF32 math) | B200SP_BF16
+    void* out;                 // [P,Q] T (FWD, DGRAD) or float (ATOMIC, accumulated)
+    // FWD
+    const float* bias;
+    int out_act;
+    const b200sp_bnfwd* bnf;
+    // DGRAD
+    const void* skip;
+    float scale_out;
+    const b200sp_bnbwd* bnb;
+    double count;
+};
+
+// returns 0 on success, B200SP_ENOSYS when the shape is outside what the tensor-core path supports
+// (the caller then uses the CUDA-core/mma.sync fallback kernel), or a cudaError_t.
+int tcgemm_launch(const TcgProblem& p, cudaStream_t st);

@@ -18,7 +18,8 @@ def _g(seed):
     return torch.Generator().manual_seed(seed)
 
 
-@pytest.mark.parametrize('M,N,K', [(301, 16, 32), (1000, 96, 16), (257, 24, 144), (2352, 320, 960), (64, 1024, 320), (5, 64, 96)])
+@pytest.mark.parametrize('M,N,K', [(301, 16, 32), (1000, 96, 16), (257, 24, 144), (2352, 320, 960), (64, 1024, 320), (5, 64, 96),
+                                   (40003, 96, 16), (2352, 1024, 1280), (20001, 144, 24), (9408, 576, 96)])
 @pytest.mark.parametrize('act', [L.ACT_NONE, L.ACT_RELU6])
 def test_pw_fwd_with_bn_epilogue(M, N, K, act):
     g = _g(M + N + K)
@@ -54,7 +55,8 @@ def test_pw_fwd_bias_act_no_bn():
     assert rel(y, torch.relu(x.double() @ w.double().t() + b.double())) < TOL
 
 
-@pytest.mark.parametrize('M,N,K', [(301, 16, 32), (999, 96, 16), (2352, 1024, 320), (130, 24, 144)])
+@pytest.mark.parametrize('M,N,K', [(301, 16, 32), (999, 96, 16), (2352, 1024, 320), (130, 24, 144), (40003, 96, 16), (20001, 24, 144),
+                                   (2352, 1024, 1280), (9408, 96, 576), (784, 64, 96)])
 @pytest.mark.parametrize('act', [L.ACT_NONE, L.ACT_RELU6, L.ACT_LEAKY02])
 def test_pw_dgrad_fused_bn_backward(M, N, K, act):
     g = _g(M * 3 + N + K + act)
@@ -101,7 +103,8 @@ def test_pw_dgrad_plain_scale():
     assert rel(out, -0.37 * (dy.double() @ w.double())) < TOL
 
 
-@pytest.mark.parametrize('M,N,K', [(3001, 16, 32), (1999, 96, 16), (2352, 1024, 320), (4097, 24, 144), (100, 64, 96)])
+@pytest.mark.parametrize('M,N,K', [(3001, 16, 32), (1999, 96, 16), (2352, 1024, 320), (4097, 24, 144), (100, 64, 96), (60003, 96, 16),
+                                   (2352, 1024, 1280), (9408, 576, 96), (37632, 32, 192), (784, 64, 96), (196, 64, 96)])
 def test_pw_wgrad(M, N, K):
     g = _g(M + 7 * N + K)
     gq, yq = torch.randn(M, N, generator=g), torch.randn(M, N, generator=g)
