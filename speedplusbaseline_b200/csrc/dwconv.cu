@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
 
 }  // namespace
 
-extern "C" int b200sp_dw_fwd(const b200sp_vtensor* x, const float* w9c, void* y, const b200sp_bnfwd* bn,
+int dw_fwd_legacy(const b200sp_vtensor* x, const float* w9c, void* y, const b200sp_bnfwd* bn,
                              int B, int H, int W, int C, int stride, int dtype, void* stream) {
     if (dtype != B200SP_F32) return B200SP_ENOSYS;
     if (!x || x->mode == B200SP_VT_DY) return B200SP_EINVAL;
@@ -479,7 +479,7 @@ extern "C" int b200sp_dw_fwd(const b200sp_vtensor* x, const float* w9c, void* y,
     B200SP_RETURN_LAST();
 }
 
-extern "C" int b200sp_dw_bwd(const b200sp_vtensor* dy, const b200sp_vtensor* x, const float* w9c, const void* skip,
+int dw_bwd_legacy(const b200sp_vtensor* dy, const b200sp_vtensor* x, const float* w9c, const void* skip,
                              void* g_in, float* dw9c, const b200sp_bnbwd* bn,
                              int B, int H, int W, int C, int stride, int dtype, void* stream) {
     if (dtype != B200SP_F32) return B200SP_ENOSYS;
