@@ -80,6 +80,29 @@ __device__ __forceinline__ Item get_item(const RGeom& gm, int sl, int rows) {
     return it;
 }
 
+// raw (untransformed) loads of one row segment; apply_row() turns them into values later, so a caller can
+// put ALL the loads of a step in flight before the first use
+template <typename T, int MODE, int NC>
+__device__ __forceinline__ void load_row_raw(const b200sp_vtensor& t, size_t img, int row, int rows, int col0, int cols,
+                                             int C, int c, float4 (&raw)[NC], float4 (&raw2)[NC]) {
+    const size_t rowoff = (img + (size_t)min(max(row, 0), rows - 1) * cols) * C + c;
+    const T* x = reinterpret_cast<const T*>(t.x);
+    const T* x2 = reinterpret_cast<const T*>(t.x2);
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        const size_t off = rowoff + (size_t)min(max(col0 + j, 0), cols - 1) * C;
+        raw[j] = Vec4<T>::ld(x + off);
+        if (MODE == XM_DY) raw2[j] = Vec4<T>::ld(x2 + off); else raw2[j] = f4zero();
+    }
+}
+template <int MODE, int NC>
+__device__ __forceinline__ void apply_row(const VtP& p, int row, int rows, int col0, int cols, const float4 (&raw)[NC],
+                                          const float4 (&raw2)[NC], float4 (&r)[NC]) {
+    const bool rok = row >= 0 && row < rows;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) r[j] = vtp_apply<MODE>(p, raw[j], raw2[j], rok && col0 + j >= 0 && col0 + j < cols);
+}
+
 // load + transform one row segment of NC pixels (4 channels each) of a virtual [rows, cols, C] image
 template <typename T, int MODE, int NC>
 __device__ __forceinline__ void load_row(const b200sp_vtensor& t, const VtP& p, size_t img, int row, int rows, int col0, int cols,
@@ -240,13 +263,15 @@ __global__ void __launch_bounds__(RNT, 3) dwr_bwd_kernel(const b200sp_vtensor dy
         for (int t = 0; t < 9; ++t) dwacc[t] = f4zero();
         const size_t oimg = (size_t)it.b * gm.Ho * gm.Wo, iimg = (size_t)it.b * gm.H * gm.W;
         // per input pixel: raw BN input (yin), conv-input value (av, for wgrad), skip gradient; loads are unconditional
-        auto pixel_loads = [&](size_t off, float4& yin, float4& av, float4& skv) {
-            yin = f4zero(); skv = f4zero();
-            float4 xr = f4zero();
+        // raw loads first (yin, conv-input, skip gradient), the conv-input VALUE av (for wgrad) afterwards
+        auto pixel_loads = [&](size_t off, float4& yin, float4& xr, float4& skv) {
+            yin = f4zero(); skv = f4zero(); xr = f4zero();
             if (cx.has_bn) yin = Vec4<T>::ld(ybn + off);
             if (!cx.same_src) xr = Vec4<T>::ld(xraw + off);
             if (cx.has_skip) skv = Vec4<T>::ld(skip + off);
-            av = cx.same_src ? f4act(f4fma(yin, cx.sc, cx.sh), cx.xact) : vtp_apply<XM>(xp, xr, f4zero(), true);
+        };
+        auto in_val = [&](float4 yin, float4 xr) {
+            return cx.same_src ? f4act(f4fma(yin, cx.sc, cx.sh), cx.xact) : vtp_apply<XM>(xp, xr, f4zero(), true);
         };
         if (S == 1) {
             constexpr int IW = 2, NC = IW + 2;
@@ -255,14 +280,17 @@ __global__ void __launch_bounds__(RNT, 3) dwr_bwd_kernel(const b200sp_vtensor dy
             load_row<T, DM, NC>(dy, dp, oimg, it.r_a - 1, gm.Ho, wi0 - 1, gm.Wo, gm.C, c, D0);
             load_row<T, DM, NC>(dy, dp, oimg, it.r_a, gm.Ho, wi0 - 1, gm.Wo, gm.C, c, D1);
             for (int hi = it.r_a; hi < it.r_b; ++hi) {
-                float4 yin[IW], av[IW], skv[IW];
+                float4 yin[IW], av[IW], skv[IW], rg[NC], ry[NC];
                 size_t offs[IW];
+                load_row_raw<T, DM, NC>(dy, oimg, hi + 1, gm.Ho, wi0 - 1, gm.Wo, gm.C, c, rg, ry);
 #pragma unroll
                 for (int o = 0; o < IW; ++o) {
                     offs[o] = (iimg + (size_t)hi * gm.W + min(wi0 + o, gm.W - 1)) * gm.C + c;
                     pixel_loads(offs[o], yin[o], av[o], skv[o]);
                 }
-                load_row<T, DM, NC>(dy, dp, oimg, hi + 1, gm.Ho, wi0 - 1, gm.Wo, gm.C, c, D2);
+                apply_row<DM, NC>(dp, hi + 1, gm.Ho, wi0 - 1, gm.Wo, rg, ry, D2);
+#pragma unroll
+                for (int o = 0; o < IW; ++o) av[o] = in_val(yin[o], av[o]);
 #pragma unroll
                 for (int o = 0; o < IW; ++o) {
                     if (wi0 + o < gm.W) {
@@ -290,8 +318,9 @@ __global__ void __launch_bounds__(RNT, 3) dwr_bwd_kernel(const b200sp_vtensor dy
             float4 E0[NB + 1], E1[NB + 1];
             load_row<T, DM, NB + 1>(dy, dp, oimg, it.r_a, gm.Ho, cb0, gm.Wo, gm.C, c, E0);
             for (int a = it.r_a; a < it.r_b; ++a) {
-                float4 yin[NB][4], av[NB][4], skv[NB][4];
+                float4 yin[NB][4], av[NB][4], skv[NB][4], rg[NB + 1], ry[NB + 1];
                 size_t offs[NB][4];
+                load_row_raw<T, DM, NB + 1>(dy, oimg, a + 1, gm.Ho, cb0, gm.Wo, gm.C, c, rg, ry);
 #pragma unroll
                 for (int j = 0; j < NB; ++j)
 #pragma unroll
@@ -300,7 +329,11 @@ __global__ void __launch_bounds__(RNT, 3) dwr_bwd_kernel(const b200sp_vtensor dy
                         offs[j][q] = (iimg + (size_t)hi * gm.W + wi) * gm.C + c;
                         pixel_loads(offs[j][q], yin[j][q], av[j][q], skv[j][q]);
                     }
-                load_row<T, DM, NB + 1>(dy, dp, oimg, a + 1, gm.Ho, cb0, gm.Wo, gm.C, c, E1);
+                apply_row<DM, NB + 1>(dp, a + 1, gm.Ho, cb0, gm.Wo, rg, ry, E1);
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) av[j][q] = in_val(yin[j][q], av[j][q]);
 #pragma unroll
                 for (int j = 0; j < NB; ++j) {
 #pragma unroll
