@@ -173,6 +173,19 @@ int b200sp_krn_loss(const float *logits, const float *target /*[B,2,N/2]*/, floa
 int b200sp_head_bwd(const float *dlogits, const b200sp_vtensor *x, const float *w, void *g, float *dw /* += */,
                     float *dbias /* += */, const b200sp_bnbwd *bn, int B, int HWC, int C, int N, int dtype, void *stream);
 
+/* ---- DANN domain classifier tail + loss (revgrad.py:75-80 AvgPool2d(7) -> Conv2d(1280,1,1); dann.py:85-92
+ * binary_cross_entropy_with_logits(mean) against a constant label).  The first conv (+bias+ReLU) is
+ * b200sp_pw_fwd.  h is [B,HW,C] NHWC. */
+int b200sp_dann_head_fwd(const void *h, const float *w3 /*[C]*/, const float *b3 /*[1]*/, float *pooled /*[B,C]*/,
+                         float *z /*[B]*/, int B, int HW, int C, int dtype, void *stream);
+/* loss[0] = mean BCE-with-logits(z, label); dz[b] = (sigmoid(z_b) - label)/B * loss_scale[0] (NULL => 1) */
+int b200sp_bce_logits(const float *z, float label, float *loss, float *dz, const float *loss_scale, int B, void *stream);
+/* h_inout <- dL/dh = dz[b]*w3[c]/HW * (h>0)  (ReLU + AvgPool backward, in place); dw3 += , db3 += */
+int b200sp_dann_head_bwd(void *h_inout, const float *dz, const float *pooled, const float *w3, float *dw3, float *db3,
+                         int B, int HW, int C, int dtype, void *stream);
+/* x *= s[0]*mul with s in DEVICE memory: the gradient-reversal factor -lambda (revgrad.py:52-56) */
+int b200sp_scale_dev(void *x, int64_t n, const float *s, float mul, int dtype, void *stream);
+
 /* ---- optimizer (build.py:72-74 torch.optim.AdamW; trainer.py:97 clip_grad_norm_) ---- */
 typedef struct b200sp_adamw_hp {   /* lives in DEVICE memory so CUDA graphs can replay */
     float lr, beta1, beta2, eps, weight_decay, max_norm, clip_value, grad_scale;

@@ -10,6 +10,7 @@ from . import _build
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_RELU6, ACT_LEAKY02, ACT_SIGMOID = 0, 1, 2, 3, 4
 VT_PLAIN, VT_BNACT, VT_DY = 0, 1, 2
+BF16_ENABLED = False      # bf16 activation storage (--use_fp16): kernels templated, entry points not opened yet
 
 vp = C.c_void_p
 
@@ -73,6 +74,10 @@ _SIGS = {
     'b200sp_head_bias': ([vp, vp, i32, i32, vp], i32),
     'b200sp_krn_loss': ([vp, vp, vp, vp, vp, vp, i32, i32, vp], i32),
     'b200sp_head_bwd': ([vp, PVT, vp, vp, vp, vp, PBB, i32, i32, i32, i32, i32, vp], i32),
+    'b200sp_dann_head_fwd': ([vp, vp, vp, vp, vp, i32, i32, i32, i32, vp], i32),
+    'b200sp_bce_logits': ([vp, f32, vp, vp, vp, i32, vp], i32),
+    'b200sp_dann_head_bwd': ([vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp], i32),
+    'b200sp_scale_dev': ([vp, i64, vp, f32, i32, vp], i32),
     'b200sp_grad_sqnorm': ([vp, i64, vp, vp], i32),
     'b200sp_adamw_step': ([vp, vp, vp, vp, vp, i64, vp, vp], i32),
 }

@@ -13,6 +13,7 @@ import time
 import torch
 
 from .. import _lib as L
+from ..dist import GradSync
 from ..utils import AverageMeter, report_progress
 
 logger = logging.getLogger("Training")
@@ -25,6 +26,9 @@ class KRNTrainStep:
     def __init__(self, model, optimizer, use_graph=True, world_size=1, process_group=None):
         self.model, self.opt, self.use_graph = model, optimizer, use_graph
         self.world, self.pg = world_size, process_group
+        self.sync = GradSync(world_size, process_group)
+        if world_size > 1:
+            optimizer.grad_scale = self.sync.grad_scale      # 1/world folded into the AdamW kernel
         self._graphs = None
         self._static = None
         self._sig = None
@@ -41,9 +45,7 @@ class KRNTrainStep:
         self.opt.step(sync=False)
 
     def _allreduce(self):
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.model.engine.store.grads, group=self.pg)
+        self.sync.allreduce(self.model.engine.store.grads)
 
     def eager(self, images, target):
         self.opt.sync_hyperparams()
@@ -117,13 +119,14 @@ def train_single_epoch_krn(epoch, cfg, model, data_loader, optimizer,
         loss3 = stepper.step(images, target)
         # read the PREVIOUS iteration's losses (already complete) instead of syncing on this one
         if pending is not None:
-            l3, pb = pending
+            l3, pb, pev = pending
+            pev.synchronize()                           # waits for the PREVIOUS step's 12-byte copy only
             loss_x_meter.update(float(l3[1]), pb)
             loss_y_meter.update(float(l3[2]), pb)
         host = torch.empty(3, pin_memory=True)
         host.copy_(loss3, non_blocking=True)
         ev = torch.cuda.Event(); ev.record()
-        pending = (host, B)
+        pending = (host, B, ev)
         training_time_meter.update((time.time() - start) * 1000, B)
         report_progress(epoch=epoch, lr=lr, epoch_iter=idx + 1, epoch_size=len(data_loader),
                         time=training_time_meter, is_train=True, loss_x=loss_x_meter, loss_y=loss_y_meter)

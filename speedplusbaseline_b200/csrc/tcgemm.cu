@@ -19,6 +19,7 @@
 // contiguous (fwd A/B, dgrad A), MN-major otherwise (dgrad B = W, wgrad A = dY and B = X), so no
 // transposed weight copies exist anywhere.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include "tcgemm.cuh"
 #include "tc_common.cuh"
 
@@ -59,6 +60,7 @@ struct TcgArgs {
     int has_bnb;
     b200sp_bnbwd bnb;
     double count;
+    int wait_mode;
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
@@ -70,10 +72,30 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // bounded spin: a protocol bug traps instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t parity, int mode = 0) {
     uint32_t spins = 0;
-    while (!tc::mbar_try_wait_hint(bar, parity, 20000u)) {      // hardware-suspended wait (no issue slots burnt)
-        if (++spins > (1u << 22)) __trap();
+    if (mode == 0) {
+        while (!tc::mbar_try_wait_hint(bar, parity, 20000u)) {      // hardware-suspended wait (no issue slots burnt)
+            if (++spins > (1u << 22)) __trap();
+        }
+    } else if (mode == 1) {
+        while (!tc::mbar_try_wait(bar, parity)) {
+            if (++spins > (1u << 26)) __trap();
+        }
+    } else {
+        while (!tc::mbar_test_wait(bar, parity)) {
+            if (++spins > (1u << 28)) __trap();
+        }
+    }
+}
+
+// long waits (the epilogue waits for a whole main loop): back off so the spin does not steal issue
+// slots from the producer warps sharing the scheduler
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!tc::mbar_try_wait(bar, parity)) {
+        __nanosleep(256);
+        if (++spins > (1u << 24)) __trap();
     }
 }
 
@@ -162,7 +184,7 @@ struct OpLoader {
     int ld, mn_ext, R, nkb, ac_last;
     int pt;
     // geometry: [0] full k-blocks, [1] the partial last k-block (K-major only)
-    int gc0, gc1, gr00, gr01, grstep0, grstep1;
+    int gc0, gc1, gr00, gr01, grstep0, grstep1, glg0, glg1;
     uint32_t gsoff0, gsoff1, gsstep0, gsstep1;
     __device__ __forceinline__ int gc(int gi) const { return gi ? gc1 : gc0; }
     __device__ __forceinline__ int gr0(int gi) const { return gi ? gr01 : gr00; }
@@ -178,10 +200,10 @@ struct OpLoader {
         ld = ld_; mn_ext = mn_ext_; R = R_; nkb = nkb_; ac_last = ac_last_; pt = pt_;
         cached_kb = -1;
         if (LAY == TCG_LAY_KM) {
-            gc0 = pt & 7; gr00 = pt >> 3; grstep0 = PROD_T >> 3;
+            gc0 = pt & 7; gr00 = pt >> 3; grstep0 = PROD_T >> 3; glg0 = 3;
             gsoff0 = tc::sw128_off(gr00, gc0); gsstep0 = grstep0 * 128;
             const int lg = ac_last > 4 ? 3 : (ac_last > 2 ? 2 : 1);
-            gc1 = pt & ((1 << lg) - 1); gr01 = pt >> lg; grstep1 = PROD_T >> lg;
+            gc1 = pt & ((1 << lg) - 1); gr01 = pt >> lg; grstep1 = PROD_T >> lg; glg1 = lg;
             gsoff1 = tc::sw128_off(gr01, gc1); gsstep1 = grstep1 * 128;
         } else {
             gc0 = gc1 = pt & 7;
@@ -213,7 +235,10 @@ struct OpLoader {
         if (LAY == TCG_LAY_KM) {
             if (gi == 1 && gc(1) >= ac_last) return 0;
             const int rem = ext - gr0(gi);
-            return rem <= 0 ? 0 : (rem + grstep(gi) - 1) / grstep(gi);
+            // grstep = PROD_T >> lg is a power of two: divide by shifting
+            constexpr int LGP = PROD_T == 256 ? 8 : 9;
+            const int sh = LGP - (gi ? glg1 : glg0);
+            return rem <= 0 ? 0 : (rem + grstep(gi) - 1) >> sh;
         }
         const int atoms = (ext * E::ES + 127) / 128;
         return E::TF32 ? atoms : 2 * atoms;
@@ -361,12 +386,11 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
             if (fetch.valid()) { issue(fetch, d); fetch.next(g); }
             cp_async_commit();
         }
-        int n = 0;
+        int rs = 0, os = 0;
+        uint32_t par = 1;
         while (cons.valid()) {
             if (g.n_raw == 4) cp_async_wait<3>(); else if (g.n_raw == 3) cp_async_wait<2>(); else cp_async_wait<1>();
-            const int rs = n % g.n_raw, os = n % g.n_op;
-            const uint32_t par = ((n / g.n_op) & 1) ^ 1;
-            mbar_wait_guard(&empty[os], par);
+            mbar_wait_guard(&empty[os], par, g.wait_mode);
             const uint32_t rbase = raw0 + rs * g.raw_stage_bytes;
             const uint32_t a_hi = s_base + os * g.op_stage_bytes, a_lo = a_hi + g.a_op_bytes;
             const uint32_t b_hi = a_hi + b_in_stage, b_lo = b_hi + g.b_op_bytes;
@@ -380,7 +404,8 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
             if (fetch.valid()) { issue(fetch, rs); fetch.next(g); }
             cp_async_commit();
             cons.next(g);
-            ++n;
+            if (++rs == g.n_raw) rs = 0;
+            if (++os == g.n_op) { os = 0; par ^= 1; }
         }
         cp_async_wait<0>();
     } else if (warp == MMA_WARP) {
@@ -398,17 +423,17 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
             return BLAY == TCG_LAY_KM ? tc::smem_desc(base + ks * KSTEP_KM, 0, 1024, tc::SWZ_128B)
                                       : tc::smem_desc(base + ks * KSTEP_MM, LBO_MM, SBO_MM, LT_MM);
         };
-        if (g.b_res) { mbar_wait_guard(bfull, 0); tc::tc_fence_after(); }
-        int n = 0, ni = 0;
+        if (g.b_res) { mbar_wait_guard(bfull, 0, g.wait_mode); tc::tc_fence_after(); }
+        int ni = 0, os = 0;
+        uint32_t fpar = 0;
         for (int it = blockIdx.x; it < total; it += gridDim.x, ++ni) {
             const Item w = get_item(g, it);
             const int acc = ni & 1;
-            mbar_wait_guard(&tempty[acc], ((ni >> 1) & 1) ^ 1);
+            mbar_wait_guard(&tempty[acc], ((ni >> 1) & 1) ^ 1, g.wait_mode);
             tc::tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * g.BN;
-            for (int kb = w.kb0; kb < w.kb1; ++kb, ++n) {
-                const int os = n % g.n_op;
-                mbar_wait_guard(&full[os], (n / g.n_op) & 1);
+            for (int kb = w.kb0; kb < w.kb1; ++kb) {
+                mbar_wait_guard(&full[os], fpar, g.wait_mode);
                 tc::tc_fence_after();
                 if (lane == 0) {
                     const uint32_t a_hi = s_base + os * g.op_stage_bytes, a_lo = a_hi + g.a_op_bytes;
@@ -430,6 +455,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
                     if (kb == w.kb1 - 1) tc::umma_commit(&tfull[acc]);
                 }
                 __syncwarp();
+                if (++os == g.n_op) { os = 0; fpar ^= 1; }
             }
         }
     } else {
@@ -473,7 +499,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
             const int acc = ni & 1;
             if (do_stats && cur_q0 >= 0 && cur_q0 != w.q0) flush(cur_q0);
             cur_q0 = w.q0;
-            mbar_wait_guard(&tfull[acc], (ni >> 1) & 1);
+            mbar_wait_sleep(&tfull[acc], (ni >> 1) & 1);
             tc::tc_fence_after();
             const uint32_t t_row = tmem_base + acc * g.BN + ((uint32_t)(lq * 32) << 16);
             if (last_chunk < 0) {                        // nothing to read for this warp: release immediately
@@ -729,6 +755,11 @@ int tcgemm_launch(const TcgProblem& p, cudaStream_t st) {
     a.has_bnb = p.bnb != nullptr;
     if (p.bnb) a.bnb = *p.bnb;
     a.count = p.count;
+    {
+        static int wm = -1;
+        if (wm < 0) { const char* e = getenv("B200SP_TCG_WAIT"); wm = e ? atoi(e) : 0; }
+        a.wait_mode = wm;
+    }
     if (p.dtype == B200SP_F32) return launch_T<float>(a, p, st);
     if (p.dtype == B200SP_BF16) return launch_T<bf16>(a, p, st);
     return B200SP_ENOSYS;

@@ -345,6 +345,49 @@ class KRNEngine:
                 dy0 = self._vt_dy(cx, g0, y0, bi0)
                 L.call('b200sp_stem_wgrad', cx.images.data_ptr(), C.byref(dy0), self._wg('base.0.0.weight'), B, cx.H, cx.W, dt, sp)
 
+    # ------------------------------------------------------------------ DANN domain classifier
+    def domain_forward(self, cx, label, loss_slot=0):
+        """revgrad.py:75-80,92-93 + dann.py:85-92 on the base[17] output of the pass recorded in `cx`:
+        GRL (identity forward) -> conv1x1 320->1280 (+bias, ReLU) -> AvgPool(7) -> conv1x1 1280->1 ->
+        mean BCE-with-logits against the constant `label` (1 source, 0 target).  Fills cx.dom_z [B],
+        cx.dom_loss [1] and the logit gradient cx.dom_dz."""
+        assert self.dann
+        B, sp, dt = cx.B, L.stream_ptr(), self.dtype
+        h, w = cx.fh, cx.fw
+        M = B * h * w
+        f32 = dict(dtype=torch.float32, device=self.device)
+        if getattr(cx, 'dom_z', None) is None or cx.dom_z.shape[0] != B:
+            cx.dom_z, cx.dom_dz = torch.zeros(B, **f32), torch.zeros(B, **f32)
+            cx.dom_pool, cx.dom_loss = torch.zeros(B, 1280, **f32), torch.zeros(1, **f32)
+        hbuf = self._buf(cx.Y, 'dom_h', (B, h, w, 1280))
+        fvt = self._vt_plain(cx.O[17])
+        L.call('b200sp_pw_fwd', C.byref(fvt), self.store.w_ptr('domain_classifier.0.weight'),
+               self.store.w_ptr('domain_classifier.0.bias'), L.ACT_RELU, hbuf.data_ptr(), None, M, 1280, 320, dt, sp)
+        L.call('b200sp_dann_head_fwd', hbuf.data_ptr(), self.store.w_ptr('domain_classifier.3.weight'),
+               self.store.w_ptr('domain_classifier.3.bias'), cx.dom_pool.data_ptr(), cx.dom_z.data_ptr(), B, h * w, 1280, dt, sp)
+        L.call('b200sp_bce_logits', cx.dom_z.data_ptr(), float(label), cx.dom_loss.data_ptr(), cx.dom_dz.data_ptr(), None, B, sp)
+        return cx.dom_z
+
+    def domain_backward(self, cx, neg_alpha_dev):
+        """Backward of domain_forward: accumulates the domain-classifier gradients and returns the
+        gradient entering base[17]'s output, already multiplied by -alpha (the gradient reversal,
+        revgrad.py:52-56; `neg_alpha_dev` is a 1-element DEVICE tensor holding -alpha)."""
+        B, sp, dt, st = cx.B, L.stream_ptr(), self.dtype, self.store
+        h, w = cx.fh, cx.fw
+        M = B * h * w
+        hbuf = cx.Y['dom_h']
+        L.call('b200sp_dann_head_bwd', hbuf.data_ptr(), cx.dom_dz.data_ptr(), cx.dom_pool.data_ptr(),
+               st.w_ptr('domain_classifier.3.weight'), st.wg_ptr('domain_classifier.3.weight'),
+               st.wg_ptr('domain_classifier.3.bias'), B, h * w, 1280, dt, sp)
+        dvt = self._vt_plain(hbuf)                           # now holds dL/d(conv0 output)
+        L.call('b200sp_pw_wgrad', C.byref(dvt), C.byref(self._vt_plain(cx.O[17])), st.wg_ptr('domain_classifier.0.weight'),
+               st.wg_ptr('domain_classifier.0.bias'), M, 1280, 320, dt, sp)
+        fg = self._buf(cx.dO, 'dom_f', cx.O[17].shape)
+        L.call('b200sp_pw_dgrad', C.byref(dvt), st.w_ptr('domain_classifier.0.weight'), None, 1.0, fg.data_ptr(), None,
+               M, 1280, 320, dt, sp)
+        L.call('b200sp_scale_dev', fg.data_ptr(), fg.numel(), neg_alpha_dev.data_ptr(), 1.0, dt, sp)
+        return fg
+
     def _convdw_bwd(self, cx, e, cin, cout, in_vt, g_in, in_bn, skip):
         """backward of extras.<e> ConvDw given g of its output BN already in cx.G['xp<e>'] (+coefs)."""
         B, h, w, sp, dt = cx.B, cx.fh, cx.fw, L.stream_ptr(), self.dtype

@@ -1,0 +1,62 @@
+"""Model / optimizer factory with the reference's contract (/root/reference/src/nets/build.py:39-78).
+
+get_model dispatches on cfg.model_name / cfg.dann exactly like the reference; get_optimizer returns the
+fused flat-buffer AdamW for `--optimizer adamw` (the north-star path; clip mode follows the loop that
+will drive it: global-norm 1.0 for KRN/DANN, trainer.py:97 / dann.py:99, value 1.0 for SPN,
+trainer.py:184).  sgd / rmsprop / adam are outside the hot path: they fall back to
+the stock torch optimizers on the module's aliased Parameters, which works because `.grad` aliases the
+flat gradient buffer.
+"""
+import logging
+
+import torch
+
+from .. import _lib as L
+from ..optim import FusedAdamW
+from .park2019 import KeypointRegressionNet
+from .revgrad import RevGrad
+
+logger = logging.getLogger(__name__)
+
+
+def _dtype(cfg):
+    return L.BF16 if getattr(cfg, 'fp16', False) and L.BF16_ENABLED else L.F32
+
+
+def get_model(cfg):
+    assert cfg.model_name == 'krn' or cfg.model_name == 'spn', \
+        'Model name must be either krn or spn'
+    device = getattr(cfg, 'device', None)
+    if not cfg.dann:
+        if cfg.model_name == 'krn':
+            model = KeypointRegressionNet(cfg.num_keypoints, device=device, dtype=_dtype(cfg))
+            logger.info('KRN created')
+        else:
+            from .spn import SpacecraftPoseNet
+            model = SpacecraftPoseNet(cfg.num_classes, pretrain=True, device=device)
+            logger.info('SPN created')
+    else:
+        model = RevGrad(cfg.num_keypoints, device=device)
+        logger.info('RevGrad created with {}'.format(cfg.model_name))
+    n = sum(p.numel() for p in model.parameters())
+    logger.info('   - Number of total parameters:     {:,}'.format(n))
+    logger.info('   - Number of trainable parameters: {:,}'.format(n))
+    return model
+
+
+def get_optimizer(cfg, model):
+    param = filter(lambda p: p.requires_grad, model.parameters())
+    if cfg.optimizer == 'sgd':
+        optimizer = torch.optim.SGD(param, lr=cfg.lr, momentum=cfg.momentum, weight_decay=cfg.weight_decay)
+    elif cfg.optimizer == 'rmsprop':
+        optimizer = torch.optim.RMSprop(param, lr=cfg.lr, alpha=cfg.momentum, weight_decay=cfg.weight_decay)
+    elif cfg.optimizer == 'adam':
+        optimizer = torch.optim.Adam(param, lr=cfg.lr, betas=(cfg.momentum, 0.999), weight_decay=cfg.weight_decay)
+    elif cfg.optimizer == 'adamw':
+        clip_mode = 2 if cfg.model_name == 'spn' and not cfg.dann else 1
+        optimizer = FusedAdamW(model._store, param, lr=cfg.lr, betas=(cfg.momentum, 0.999),
+                               weight_decay=cfg.weight_decay, clip_mode=clip_mode, max_norm=1.0, clip_value=1.0)
+    else:
+        raise AssertionError('unknown optimizer %r' % cfg.optimizer)
+    logger.info('Optimizer created: {}'.format(cfg.optimizer))
+    return optimizer
