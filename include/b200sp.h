@@ -173,6 +173,54 @@ int b200sp_krn_loss(const float *logits, const float *target /*[B,2,N/2]*/, floa
 int b200sp_head_bwd(const float *dlogits, const b200sp_vtensor *x, const float *w, void *g, float *dw /* += */,
                     float *dbias /* += */, const b200sp_bnbwd *bn, int B, int HWC, int C, int N, int dtype, void *stream);
 
+/* ---- style augmentation (src/styleaug/ghiasi.py:6-135, styleAugmentor.py:44-68), forward only -------------- */
+/* Dense k x k convolution as a shifted GEMM on tcgen05 with TMA-staged bf16 operands (csrc/convtc.cu).
+ * Replaces ReflectionPad2d + Conv2d (ghiasi.py:11-12,36-37,73-81) and Upsample + ... (ghiasi.py:34-37): padding,
+ * stride-2 phase split and nearest upsampling are materialised by whoever wrote the input planes
+ * (b200sp_in_apply / b200sp_sa_prep).  planes[p]: bf16 [B*Hq*Wq (+8 rows of slack)][C]; chunk j contributes
+ * plane rows m + shift_j, 128 bytes starting at channel c0_j, against weight columns [64j, 64j+64) of
+ * w = bf16 [N_pad][64*n_chunks].  out: fp32 [B][Ho][Wo][N_out]; stats (may be NULL): fp32 [B][2][N_pad]
+ * accumulated (+=) per-(image, channel) sum and sum of squares over the Ho*Wo valid outputs. */
+#define B200SP_CONVTC_MAX_CHUNKS 64
+typedef struct b200sp_convtc_chunk { int32_t plane, c0, shift, pad_; } b200sp_convtc_chunk;
+typedef struct b200sp_convtc_desc {
+    const void *planes[4];
+    const void *w;
+    float *out;
+    float *stats;
+    int32_t C, B, Hq, Wq, Ho, Wo, N_pad, N_out, n_chunks, pad_;
+    b200sp_convtc_chunk chunks[B200SP_CONVTC_MAX_CHUNKS];
+} b200sp_convtc_desc;
+int b200sp_convtc_fwd(const b200sp_convtc_desc *d, void *stream);
+
+/* NCHW fp32 image [B,3,H,W] -> reflection-padded NHWC bf16 plane [B][H+2p][W+2p][Cd] (channels >= 3 zero) */
+int b200sp_sa_prep(const float *x_nchw, void *plane, int B, int H, int W, int pad, int Cd, void *stream);
+/* InstanceNorm2d(affine=False, eps) statistics -> per-(image, channel) scale/shift, folding the conditional
+ * gamma/beta (ghiasi.py:57-61,94-103; NULL => 1/0):  scale = gamma*rstd, shift = beta - mean*scale.
+ * gamma/beta: [B][gb_stride] rows.  Re-zeroes stats. */
+int b200sp_in_finalize(float *stats, const float *gamma, const float *beta, int gb_stride, float *scale, float *shift,
+                       int B, int C, int N_pad, int HW, float eps, void *stream);
+/* v = act(raw*scale + shift) (+ res_in), written (a) as the NEXT conv's bf16 input plane(s): reflection padding
+ * `pad`, nearest upsampling `up` (1|2), stride-2 phase split `ps` (1|2 -> 1|4 planes of [B][Hd][Wd][Cd]);
+ * (b) optionally as the fp32 residual stream res_out [B][Hs][Ws][C] (interior pixels, ps == up == 1 only). */
+typedef struct b200sp_in_apply_desc {
+    const float *raw;        /* [B][Hs][Ws][Cs] */
+    const float *scale, *shift;   /* [B][C] */
+    const float *res_in;     /* fp32 [B][Hs][Ws][C] or NULL */
+    float *res_out;          /* or NULL */
+    void *planes[4];
+    int32_t B, Hs, Ws, Cs, C, act, pad, up, ps, Hd, Wd, Cd;
+} b200sp_in_apply_desc;
+int b200sp_in_apply(const b200sp_in_apply_desc *d, void *stream);
+/* last layer (ghiasi.py:135): out_nchw[b,c,h,w] = sigmoid(raw[b,h,w,c]*scale[b,c] + shift[b,c]), c < C */
+int b200sp_in_apply_final(const float *raw, const float *scale, const float *shift, float *out_nchw,
+                          int B, int H, int W, int Cs, int C, void *stream);
+/* e = alpha*(noise A^T + mean) + (1-alpha)*base  (styleAugmentor.py:44-64); all fp32, A [D][D] row-major */
+int b200sp_style_embed(const float *noise, const float *A, const float *mean, const float *base, float alpha,
+                       float *out, int B, int D, void *stream);
+/* out[b][t] = sum_d emb[b][d] W[t][d] + bias[t]: the 26 Linear(100->C) of ghiasi.py:50-51,87-90 concatenated */
+int b200sp_style_linear(const float *emb, const float *W, const float *bias, float *out, int B, int D, int T, void *stream);
+
 /* ---- DANN domain classifier tail + loss (revgrad.py:75-80 AvgPool2d(7) -> Conv2d(1280,1,1); dann.py:85-92
  * binary_cross_entropy_with_logits(mean) against a constant label).  The first conv (+bias+ReLU) is
  * b200sp_pw_fwd.  h is [B,HW,C] NHWC. */

@@ -38,6 +38,26 @@ class AdamWHp(C.Structure):
                 ('sqnorm', C.c_double), ('last_norm', C.c_float), ('pad_', C.c_float)]
 
 
+class ConvChunk(C.Structure):
+    _fields_ = [('plane', C.c_int32), ('c0', C.c_int32), ('shift', C.c_int32), ('pad_', C.c_int32)]
+
+
+CONVTC_MAX_CHUNKS = 64
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [('planes', vp * 4), ('w', vp), ('out', vp), ('stats', vp),
+                ('C', C.c_int32), ('B', C.c_int32), ('Hq', C.c_int32), ('Wq', C.c_int32), ('Ho', C.c_int32), ('Wo', C.c_int32),
+                ('N_pad', C.c_int32), ('N_out', C.c_int32), ('n_chunks', C.c_int32), ('pad_', C.c_int32),
+                ('chunks', ConvChunk * CONVTC_MAX_CHUNKS)]
+
+
+class InApplyDesc(C.Structure):
+    _fields_ = [('raw', vp), ('scale', vp), ('shift', vp), ('res_in', vp), ('res_out', vp), ('planes', vp * 4),
+                ('B', C.c_int32), ('Hs', C.c_int32), ('Ws', C.c_int32), ('Cs', C.c_int32), ('C', C.c_int32), ('act', C.c_int32),
+                ('pad', C.c_int32), ('up', C.c_int32), ('ps', C.c_int32), ('Hd', C.c_int32), ('Wd', C.c_int32), ('Cd', C.c_int32)]
+
+
 def _load():
     path = _build.LIB
     if not os.path.exists(path):
@@ -74,6 +94,13 @@ _SIGS = {
     'b200sp_head_bias': ([vp, vp, i32, i32, vp], i32),
     'b200sp_krn_loss': ([vp, vp, vp, vp, vp, vp, i32, i32, vp], i32),
     'b200sp_head_bwd': ([vp, PVT, vp, vp, vp, vp, PBB, i32, i32, i32, i32, i32, vp], i32),
+    'b200sp_convtc_fwd': ([C.POINTER(ConvDesc), vp], i32),
+    'b200sp_sa_prep': ([vp, vp, i32, i32, i32, i32, i32, vp], i32),
+    'b200sp_in_finalize': ([vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, f32, vp], i32),
+    'b200sp_in_apply': ([C.POINTER(InApplyDesc), vp], i32),
+    'b200sp_in_apply_final': ([vp, vp, vp, vp, i32, i32, i32, i32, i32, vp], i32),
+    'b200sp_style_embed': ([vp, vp, vp, vp, f32, vp, i32, i32, vp], i32),
+    'b200sp_style_linear': ([vp, vp, vp, vp, i32, i32, i32, vp], i32),
     'b200sp_dann_head_fwd': ([vp, vp, vp, vp, vp, i32, i32, i32, i32, vp], i32),
     'b200sp_bce_logits': ([vp, f32, vp, vp, vp, i32, vp], i32),
     'b200sp_dann_head_bwd': ([vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp], i32),

@@ -1,0 +1,246 @@
+"""Ghiasi style-transfer network, forward only -- the layer plan, HBM buffers and launch sequence behind
+StyleAugmentor.  Mirrors /root/reference/src/styleaug/ghiasi.py:106-135 (ConvInRelu :6-23,
+UpsampleConvInRelu :26-62, ResidualBlock :65-103); every op is a libb200sp launch (include/b200sp.h).
+
+Per convolution:   b200sp_convtc_fwd (TMA + tcgen05 shifted GEMM, bf16 operands, fp32 accumulate; raw fp32
+output + InstanceNorm sums in its epilogue)  ->  b200sp_in_finalize (scale/shift per image & channel, folding
+the style-conditional gamma/beta)  ->  b200sp_in_apply (normalise + affine + ReLU (+ residual), written
+directly in the NEXT convolution's input layout: reflection padding, x2 nearest upsampling and the stride-2
+phase split are destination-side index arithmetic).  The conv biases of the reference are dropped: each conv
+feeds a mean-subtracting InstanceNorm, so they cancel exactly."""
+import ctypes as C
+
+import torch
+
+from .. import _lib as L
+
+EPS = 1e-5            # nn.InstanceNorm2d default
+
+
+def cond_sets():
+    """conditional-instance-norm parameter sets in packing order: (state_dict prefix, suffix, C)"""
+    out = []
+    for i in range(3, 8):
+        out += [('layers.%d' % i, '1', 128), ('layers.%d' % i, '2', 128)]
+    out += [('layers.8', '', 64), ('layers.9', '', 32), ('layers.10', '', 3)]
+    return out
+
+
+def plan_chunks(k, ps, Cin, Cp, Wq):
+    """K-chunk list of the shifted GEMM.  Returns (chunks [(plane, c0, shift)], cols [[(kh, kw, c) | None] * 64])."""
+    cbox = min(Cp, 64)
+    P = 64 // cbox
+    chunks, cols = [], []
+    for kh in range(k):
+        qy, dh = kh % ps, kh // ps
+        for qx in range(ps):
+            dws = {kw // ps: kw for kw in range(k) if kw % ps == qx}
+            if not dws:
+                continue
+            for dw0 in range(0, max(dws) + 1, P):
+                for cc in range(0, Cp, cbox):
+                    ent = []
+                    for p in range(P):
+                        kw = dws.get(dw0 + p)
+                        for c in range(cbox):
+                            ent.append((kh, kw, cc + c) if (kw is not None and cc + c < Cin) else None)
+                    chunks.append((qy * ps + qx, cc, dh * Wq + dw0))
+                    cols.append(ent)
+    return chunks, cols
+
+
+def pack_weight(w, cols, N_pad):
+    """OIHW fp32 conv weight -> bf16 [N_pad][64*n_chunks] in chunk order (zeros for padding taps/channels)."""
+    Co = w.shape[0]
+    K = 64 * len(cols)
+    idx = torch.zeros(K, dtype=torch.long)
+    mask = torch.zeros(K, dtype=torch.bool)
+    kk = w.shape[2]
+    for j, ent in enumerate(cols):
+        for i, e in enumerate(ent):
+            if e is not None:
+                kh, kw, c = e
+                idx[j * 64 + i] = (c * kk + kh) * kk + kw
+                mask[j * 64 + i] = True
+    flat = w.reshape(Co, -1).float().cpu()
+    m = torch.zeros(N_pad, K, dtype=torch.float32)
+    m[:Co] = flat[:, idx] * mask.float()[None, :]
+    return m.to(torch.bfloat16).contiguous()
+
+
+class _Conv:
+    """one convolution: packed weights, chunk plan, descriptor (rebuilt when the geometry changes)."""
+
+    def __init__(self, name, w, k, stride, Cp, device):
+        self.name, self.k, self.ps, self.Cp = name, k, stride, Cp
+        self.Co, self.Ci = w.shape[0], w.shape[1]
+        self.N_pad = max(16, (self.Co + 15) // 16 * 16)
+        self.N_out = (self.Co + 3) // 4 * 4
+        self.w_ref = w
+        self.device = device
+        self._geo = None
+
+    def setup(self, B, Hq, Wq, Ho, Wo, planes, out, stats):
+        geo = (B, Hq, Wq, Ho, Wo)
+        if self._geo != geo:
+            chunks, cols = plan_chunks(self.k, self.ps, self.Ci, self.Cp, Wq)
+            assert len(chunks) <= L.CONVTC_MAX_CHUNKS, (self.name, len(chunks))
+            self.wp = pack_weight(self.w_ref, cols, self.N_pad).to(self.device)
+            self.chunks = chunks
+            self._geo = geo
+        d = L.ConvDesc()
+        for i in range(4):
+            d.planes[i] = planes[i].data_ptr() if i < len(planes) else None
+        d.w, d.out, d.stats = self.wp.data_ptr(), out.data_ptr(), (stats.data_ptr() if stats is not None else None)
+        d.C, d.B, d.Hq, d.Wq, d.Ho, d.Wo = self.Cp, B, Hq, Wq, Ho, Wo
+        d.N_pad, d.N_out, d.n_chunks = self.N_pad, self.N_out, len(self.chunks)
+        for j, (pl, c0, sh) in enumerate(self.chunks):
+            d.chunks[j].plane, d.chunks[j].c0, d.chunks[j].shift = pl, c0, sh
+        self.desc = d
+        return d
+
+
+class GhiasiEngine:
+    def __init__(self, state_dict, device):
+        L.require_cuda()
+        self.device = torch.device(device)
+        sd = {k: v.detach().float().cpu() for k, v in state_dict.items()}
+        dev = self.device
+        self.convs = {}
+
+        def add(name, key, k, stride, Cp):
+            self.convs[name] = _Conv(name, sd[key], k, stride, Cp, dev)
+
+        add('c0', 'layers.0.conv.weight', 9, 1, 8)
+        add('c1', 'layers.1.conv.weight', 3, 2, 32)
+        add('c2', 'layers.2.conv.weight', 3, 2, 64)
+        for i in range(3, 8):
+            add('r%da' % i, 'layers.%d.conv1.weight' % i, 3, 1, 128)
+            add('r%db' % i, 'layers.%d.conv2.weight' % i, 3, 1, 128)
+        add('c8', 'layers.8.conv.weight', 3, 1, 128)
+        add('c9', 'layers.9.conv.weight', 3, 1, 64)
+        add('c10', 'layers.10.conv.weight', 9, 1, 32)
+        # the 26 Linear(100 -> C) of the conditional instance norms, concatenated: per set [gamma | beta]
+        Ws, bs, self.gb_off, off = [], [], {}, 0
+        for p, sfx, Cc in cond_sets():
+            for gname in ('gamma', 'beta'):
+                Ws.append(sd['%s.fc_%s%s.weight' % (p, gname, sfx)])
+                bs.append(sd['%s.fc_%s%s.bias' % (p, gname, sfx)])
+            self.gb_off[(p, sfx)] = (off, off + Cc)
+            off += 2 * Cc
+        self.T = off
+        self.Wcat = torch.cat(Ws, 0).contiguous().to(dev)            # [T][100]
+        self.bcat = torch.cat(bs, 0).contiguous().to(dev)
+        self._bufs = {}
+        self._keep = []
+
+    # ------------------------------------------------------------------ buffers
+    def _buf(self, name, shape, dtype, zero=False):
+        t = self._bufs.get(name)
+        n = 1
+        for s in shape:
+            n *= s
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.zeros(n, dtype=dtype, device=self.device)
+            self._bufs[name] = t
+        return t[:n].view(shape)
+
+    def _plane(self, name, B, Hd, Wd, Cd):
+        # 16 pixels of slack: narrow-channel planes are read a few pixels past the last row (zero weights)
+        t = self._buf(name, (B * Hd * Wd + 16, Cd), torch.bfloat16)
+        return t
+
+    # ------------------------------------------------------------------ one conv + norm
+    def _conv(self, name, planes, B, Hq, Wq, Ho, Wo):
+        cv = self.convs[name]
+        raw = self._buf('raw_%dx%dx%d' % (Ho, Wo, cv.N_out), (B, Ho, Wo, cv.N_out), torch.float32)
+        stats = self._buf('stats_%d' % cv.N_pad, (B, 2, cv.N_pad), torch.float32)
+        d = cv.setup(B, Hq, Wq, Ho, Wo, planes, raw, stats)
+        self._keep.append(d)
+        L.call('b200sp_convtc_fwd', C.byref(d), L.stream_ptr())
+        return raw, stats, cv
+
+    def _finalize(self, stats, cv, B, HW, gb, key):
+        Cc = cv.Co
+        scale = self._buf('scale', (B, 128), torch.float32).view(-1)[:B * Cc]
+        shift = self._buf('shift', (B, 128), torch.float32).view(-1)[:B * Cc]
+        if key is None:
+            g = b = None
+        else:
+            og, ob = self.gb_off[key]
+            g, b = gb.data_ptr() + 4 * og, gb.data_ptr() + 4 * ob
+        L.call('b200sp_in_finalize', stats.data_ptr(), g, b, self.T, scale.data_ptr(), shift.data_ptr(), B, Cc, cv.N_pad, HW, EPS,
+               L.stream_ptr())
+        return scale, shift
+
+    def _apply(self, raw, scale, shift, B, Hs, Ws, Cc, act, pad, up, ps, dst_name, Cd=None, res_in=None, res_out=None):
+        Cd = Cd or Cc
+        Hd, Wd = (Hs * up + 2 * pad) // ps, (Ws * up + 2 * pad) // ps
+        planes = [self._plane('%s_%d' % (dst_name, q), B, Hd, Wd, Cd) for q in range(ps * ps)]
+        d = L.InApplyDesc()
+        d.raw, d.scale, d.shift = raw.data_ptr(), scale.data_ptr(), shift.data_ptr()
+        d.res_in = res_in.data_ptr() if res_in is not None else None
+        d.res_out = res_out.data_ptr() if res_out is not None else None
+        for q in range(4):
+            d.planes[q] = planes[q].data_ptr() if q < len(planes) else None
+        d.B, d.Hs, d.Ws, d.Cs, d.C, d.act = B, Hs, Ws, raw.shape[-1], Cc, act
+        d.pad, d.up, d.ps, d.Hd, d.Wd, d.Cd = pad, up, ps, Hd, Wd, Cd
+        self._keep.append(d)
+        L.call('b200sp_in_apply', C.byref(d), L.stream_ptr())
+        return planes, Hd, Wd
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x, embedding, out=None):
+        """x [B,3,H,W] fp32 NCHW in [0,1] on device, embedding [B,100] fp32 on device -> [B,3,H,W] in (0,1)."""
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        B, _, H, W = x.shape
+        assert H % 4 == 0 and W % 4 == 0 and H >= 16 and W >= 16, 'style net needs H, W multiples of 4'
+        sp = L.stream_ptr()
+        self._keep.clear()
+        gb = self._buf('gb', (B, self.T), torch.float32)
+        L.call('b200sp_style_linear', embedding.data_ptr(), self.Wcat.data_ptr(), self.bcat.data_ptr(), gb.data_ptr(), B, 100, self.T, sp)
+        # layer 0: reflpad 4 + conv 9x9 3->32 + IN + ReLU
+        p0 = self._plane('p0', B, H + 8, W + 8, 8)
+        L.call('b200sp_sa_prep', x.data_ptr(), p0.data_ptr(), B, H, W, 4, 8, sp)
+        raw, st, cv = self._conv('c0', [p0], B, H + 8, W + 8, H, W)
+        sc, sh = self._finalize(st, cv, B, H * W, gb, None)
+        pl, Hd, Wd = self._apply(raw, sc, sh, B, H, W, 32, L.ACT_RELU, 1, 1, 2, 'p1')
+        # layer 1: 3x3 s2 32->64
+        H1, W1 = H // 2, W // 2
+        raw, st, cv = self._conv('c1', pl, B, Hd, Wd, H1, W1)
+        sc, sh = self._finalize(st, cv, B, H1 * W1, gb, None)
+        pl, Hd, Wd = self._apply(raw, sc, sh, B, H1, W1, 64, L.ACT_RELU, 1, 1, 2, 'p2')
+        # layer 2: 3x3 s2 64->128; its output is the first residual-stream tensor
+        H2, W2 = H1 // 2, W1 // 2
+        raw, st, cv = self._conv('c2', pl, B, Hd, Wd, H2, W2)
+        sc, sh = self._finalize(st, cv, B, H2 * W2, gb, None)
+        rs = [self._buf('rs0', (B, H2, W2, 128), torch.float32), self._buf('rs1', (B, H2, W2, 128), torch.float32)]
+        pl, Hd, Wd = self._apply(raw, sc, sh, B, H2, W2, 128, L.ACT_RELU, 1, 1, 1, 'pa', res_out=rs[0])
+        cur = 0
+        for i in range(3, 8):
+            p = 'layers.%d' % i
+            raw, st, cv = self._conv('r%da' % i, pl, B, Hd, Wd, H2, W2)
+            sc, sh = self._finalize(st, cv, B, H2 * W2, gb, (p, '1'))
+            plb, _, _ = self._apply(raw, sc, sh, B, H2, W2, 128, L.ACT_RELU, 1, 1, 1, 'pb')
+            raw, st, cv = self._conv('r%db' % i, plb, B, Hd, Wd, H2, W2)
+            sc, sh = self._finalize(st, cv, B, H2 * W2, gb, (p, '2'))
+            if i < 7:
+                pl, Hd, Wd = self._apply(raw, sc, sh, B, H2, W2, 128, L.ACT_NONE, 1, 1, 1, 'pa', res_in=rs[cur], res_out=rs[cur ^ 1])
+                cur ^= 1
+            else:   # block 7 feeds the first upsampling conv: x2 nearest + reflpad 1
+                pl, Hd, Wd = self._apply(raw, sc, sh, B, H2, W2, 128, L.ACT_NONE, 1, 2, 1, 'pu8', res_in=rs[cur])
+        # layer 8: up x2 + 3x3 128->64, cond IN, ReLU
+        raw, st, cv = self._conv('c8', pl, B, Hd, Wd, H1, W1)
+        sc, sh = self._finalize(st, cv, B, H1 * W1, gb, ('layers.8', ''))
+        pl, Hd, Wd = self._apply(raw, sc, sh, B, H1, W1, 64, L.ACT_RELU, 1, 2, 1, 'pu9')
+        # layer 9: up x2 + 3x3 64->32, cond IN, ReLU; next conv is 9x9 -> reflpad 4
+        raw, st, cv = self._conv('c9', pl, B, Hd, Wd, H, W)
+        sc, sh = self._finalize(st, cv, B, H * W, gb, ('layers.9', ''))
+        pl, Hd, Wd = self._apply(raw, sc, sh, B, H, W, 32, L.ACT_RELU, 4, 1, 1, 'p10')
+        # layer 10: 9x9 32->3, cond IN, sigmoid
+        raw, st, cv = self._conv('c10', pl, B, Hd, Wd, H, W)
+        sc, sh = self._finalize(st, cv, B, H * W, gb, ('layers.10', ''))
+        if out is None:
+            out = torch.empty(B, 3, H, W, dtype=torch.float32, device=self.device)
+        L.call('b200sp_in_apply_final', raw.data_ptr(), sc.data_ptr(), sh.data_ptr(), out.data_ptr(), B, H, W, raw.shape[-1], 3, sp)
+        return out
