@@ -25,10 +25,12 @@
 
 namespace {
 
-constexpr int EPI_T = 256, MMA_T = 32, PROD_T = 256;
-constexpr int EPI_W = EPI_T / 32;               // 8 epilogue warps: warp w reads TMEM lane quarter w%4, column chunks of parity w/4
+constexpr int EPI_T = 256, MMA_T = 32, PROD_T = 512;
+constexpr int APT = 1024 / PROD_T;              // 16-byte pieces of a 128-row x 128-byte tile per producer thread
+constexpr int EPI_W = EPI_T / 32;               // epilogue warps: warp w reads TMEM lane quarter w%4; with 8 warps the column chunks are split by parity w/4
+constexpr int EPI_SETS = EPI_W / 4;
 constexpr int MMA_WARP = EPI_W;
-constexpr int NT = EPI_T + MMA_T + PROD_T;     // 544 threads: warps 0-7 epilogue, 8 MMA, 9-16 producers
+constexpr int NT = EPI_T + MMA_T + PROD_T;     // 672 threads: warps 0-3 epilogue, 4 MMA, 5-20 producers (the operand transform is latency-bound: it needs the warps)
 constexpr int BM = 128;
 constexpr int STG_LD = 36;                      // floats per epilogue staging row (32 + pad, 16B aligned)
 constexpr int MAX_OP = 4, MAX_RAW = 4;
@@ -69,7 +71,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool v
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_T) : "memory"); }
 
 // bounded spin: a protocol bug traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t parity, int mode = 0) {
@@ -168,116 +170,132 @@ __device__ __forceinline__ float4 xf_apply(float4 x, float4 x2, const XfP& p, Ac
 }
 
 // ---- operand loader: one producer thread's share of an operand tile ---------------------------------
-// The 16-byte pieces of a tile are dealt to the 256 producer threads so that each thread owns a fixed
-// (row, chunk) pattern:   piece i (i = 0..np-1) lives at operand-smem offset soff0 + i*sstep.
-//   K-major : chunk c = pt & (AC-1), rows r0 + i*rstep  (AC = active chunks per row, a power of two: a
-//             partial last k-block only converts what the MMA will read); channel = reduction index,
-//             identical for all of a thread's pieces -> transform parameters are fetched once per k-block.
-//   MN-major: chunk c = pt & 7, reduction row r0 (+32 for odd i with bf16), M/N atom i (i>>1 for bf16);
-//             channel = M/N index, fetched per piece.
-template <typename T, int LAY, int MODE>
+// The 16-byte pieces of a tile are dealt to the 512 producer threads so that each thread owns a fixed
+// (row, chunk) pattern; piece i (i < np) lives at operand-smem offset soff + i*8192 and in this thread's
+// private raw slot i.  Everything that depends only on the TILE (global offsets, validity bits) is computed
+// once per tile by begin(); per k-block the loader adds kb*kstride -- the main loop carries no index math.
+//   K-major : chunk gc = pt & 7 of row  (pt >> 3) + 64 i;  channel = reduction index = kb*KE + gc*EPV,
+//             the same for all of a thread's pieces: parameters are fetched once per k-block (early, so
+//             the load overlaps the barrier waits).
+//   MN-major: chunk gc of reduction row (pt >> 3) & (KE-1);  M/N atom 2i + (pt >> 8) for tf32 (32-row
+//             k-blocks), atom i for bf16;  channel = M/N index, fixed per piece for a whole tile.
+template <typename T, int LAY, int MODE, int NP>
 struct OpLoader {
     using E = ET<T>;
+    static constexpr int MNA = 128 / E::ES;                                   // M/N elements per 128-byte atom
+    static constexpr int ASTEP = (LAY == TCG_LAY_MM && E::TF32) ? 2 : 1;      // atoms between a thread's pieces
+    struct FTile { size_t off[NP]; uint32_t ok; };                            // fetch side
+    struct CTile { uint32_t ok; int ch0; };                                   // convert side
     b200sp_vtensor vt;
     const char *x, *x2;
     ActP act;
     int ld, mn_ext, R, nkb, ac_last;
-    int pt;
-    // geometry: [0] full k-blocks, [1] the partial last k-block (K-major only)
-    int gc0, gc1, gr00, gr01, grstep0, grstep1, glg0, glg1;
-    uint32_t gsoff0, gsoff1, gsstep0, gsstep1;
-    __device__ __forceinline__ int gc(int gi) const { return gi ? gc1 : gc0; }
-    __device__ __forceinline__ int gr0(int gi) const { return gi ? gr01 : gr00; }
-    __device__ __forceinline__ int grstep(int gi) const { return gi ? grstep1 : grstep0; }
-    __device__ __forceinline__ uint32_t gsoff(int gi) const { return gi ? gsoff1 : gsoff0; }
-    __device__ __forceinline__ uint32_t gsstep(int gi) const { return gi ? gsstep1 : gsstep0; }
-    int cached_kb;
-    XfP par;
+    int gc, row, abase, np;
+    uint32_t soff;
+    size_t kstride;
+    XfP par, par2;
 
-    __device__ __forceinline__ void init(const b200sp_vtensor& t, int ld_, int mn_ext_, int R_, int nkb_, int ac_last_, int pt_) {
+    __device__ __forceinline__ void init(const b200sp_vtensor& t, int ld_, int mn_ext_, int R_, int nkb_, int ac_last_, int pt,
+                                         int tile_rows) {
         vt = t; x = reinterpret_cast<const char*>(t.x); x2 = reinterpret_cast<const char*>(t.x2);
         act = act_params(t.act);
-        ld = ld_; mn_ext = mn_ext_; R = R_; nkb = nkb_; ac_last = ac_last_; pt = pt_;
-        cached_kb = -1;
+        ld = ld_; mn_ext = mn_ext_; R = R_; nkb = nkb_; ac_last = ac_last_;
+        gc = pt & 7;
         if (LAY == TCG_LAY_KM) {
-            gc0 = pt & 7; gr00 = pt >> 3; grstep0 = PROD_T >> 3; glg0 = 3;
-            gsoff0 = tc::sw128_off(gr00, gc0); gsstep0 = grstep0 * 128;
-            const int lg = ac_last > 4 ? 3 : (ac_last > 2 ? 2 : 1);
-            gc1 = pt & ((1 << lg) - 1); gr01 = pt >> lg; grstep1 = PROD_T >> lg; glg1 = lg;
-            gsoff1 = tc::sw128_off(gr01, gc1); gsstep1 = grstep1 * 128;
+            row = pt >> 3; abase = 0;
+            soff = tc::sw128_off(row, gc);
+            kstride = 128;
+            const int rem = tile_rows - row;
+            np = rem <= 0 ? 0 : (rem + 63) >> 6;
         } else {
-            gc0 = gc1 = pt & 7;
-            gr00 = gr01 = pt >> 3;
-            grstep0 = grstep1 = 0;
-            gsoff0 = gsoff1 = E::TF32 ? tc::sw128b32_off(pt >> 3, pt & 7) : tc::sw128_off(pt >> 3, pt & 7);
-            gsstep0 = gsstep1 = 4096;
+            const int atoms = (tile_rows * E::ES + 127) / 128;
+            if (E::TF32) {
+                row = (pt >> 3) & 31; abase = pt >> 8;
+                soff = tc::sw128b32_off(row, gc) + abase * 4096;
+                np = (atoms - abase + 1) >> 1;
+            } else {
+                row = pt >> 3; abase = 0;
+                soff = tc::sw128_off(row, gc);
+                np = atoms;
+            }
+            kstride = (size_t)E::KE * ld * E::ES;
+        }
+        if (np > NP) np = NP;
+        if (np < 0) np = 0;
+    }
+    __device__ __forceinline__ void begin(FTile& f, int mn0) const {
+        f.ok = 0;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            if (LAY == TCG_LAY_KM) {
+                const int mn = mn0 + row + 64 * i;
+                f.off[i] = ((size_t)mn * ld + gc * E::EPV) * E::ES;
+                if (mn < mn_ext) f.ok |= 1u << i;
+            } else {
+                const int mn = mn0 + (ASTEP * i + abase) * MNA + gc * E::EPV;
+                f.off[i] = ((size_t)row * ld + mn) * E::ES;
+                if (mn < mn_ext) f.ok |= 1u << i;
+            }
         }
     }
-    // source of piece i of k-block kb for the tile starting at M/N index mn0
-    __device__ __forceinline__ bool src(int kb, int mn0, int i, int gi, size_t& boff, int& ch) const {
-        int mn, red;
-        if (LAY == TCG_LAY_KM) {
-            mn = mn0 + gr0(gi) + i * grstep(gi);
-            red = kb * E::KE + gc(gi) * E::EPV;
-            ch = red;
-            boff = ((size_t)mn * ld + red) * E::ES;
-            return mn < mn_ext && red < R && (gi == 0 || gc(gi) < ac_last);
+    __device__ __forceinline__ void begin(CTile& c, int mn0) const {
+        c.ok = 0;
+        c.ch0 = mn0 + abase * MNA + gc * E::EPV;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            const int mn = LAY == TCG_LAY_KM ? mn0 + row + 64 * i : c.ch0 + ASTEP * MNA * i;
+            if (mn < mn_ext) c.ok |= 1u << i;
         }
-        if (E::TF32) { red = kb * E::KE + gr0(0); mn = mn0 + i * 32 + gc(0) * 4; }
-        else         { red = kb * E::KE + gr0(0) + 32 * (i & 1); mn = mn0 + (i >> 1) * 64 + gc(0) * 8; }
-        ch = mn;
-        boff = ((size_t)red * ld + mn) * E::ES;
-        return mn < mn_ext && red < R;
     }
-    __device__ __forceinline__ int geom(int kb) const { return (LAY == TCG_LAY_KM && kb == nkb - 1 && ac_last != 8) ? 1 : 0; }
-    // number of pieces this thread owns for a tile `ext` M/N elements wide
-    __device__ __forceinline__ int count(int gi, int ext) const {
-        if (LAY == TCG_LAY_KM) {
-            if (gi == 1 && gc(1) >= ac_last) return 0;
-            const int rem = ext - gr0(gi);
-            // grstep = PROD_T >> lg is a power of two: divide by shifting
-            constexpr int LGP = PROD_T == 256 ? 8 : 9;
-            const int sh = LGP - (gi ? glg1 : glg0);
-            return rem <= 0 ? 0 : (rem + grstep(gi) - 1) >> sh;
-        }
-        const int atoms = (ext * E::ES + 127) / 128;
-        return E::TF32 ? atoms : 2 * atoms;
+    // does this thread have anything to do for k-block kb?  (K-major: the partial last k-block only holds
+    // ac_last chunks;  MN-major: reduction rows beyond R are zero-filled)
+    __device__ __forceinline__ bool active(int kb) const {
+        return LAY == TCG_LAY_KM ? (kb != nkb - 1 || gc < ac_last) : true;
+    }
+    __device__ __forceinline__ bool kb_ok(int kb) const {
+        return LAY == TCG_LAY_KM ? (kb * E::KE + gc * E::EPV < R) : (kb * E::KE + row < R);
     }
     // cp.async this thread's raw pieces of k-block kb into its private slots (slot i at raw + i*PROD_T*16)
-    template <int NP>
-    __device__ __forceinline__ void issue(int kb, int mn0, int np, uint32_t raw, uint32_t raw2) const {
-        const int gi = geom(kb);
+    __device__ __forceinline__ void issue(int kb, const FTile& f, uint32_t raw, uint32_t raw2) const {
+        if (!active(kb)) return;
+        const bool kok = kb_ok(kb);
+        const size_t kofs = (size_t)kb * kstride;
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
             if (i < np) {
-                size_t boff; int ch;
-                const bool ok = src(kb, mn0, i, gi, boff, ch);
-                cp_async16(raw + i * (PROD_T * 16), x + (ok ? boff : 0), ok);
-                if (MODE == XM_DY) cp_async16(raw2 + i * (PROD_T * 16), x2 + (ok ? boff : 0), ok);
+                const bool ok = kok && ((f.ok >> i) & 1u);
+                const size_t o = ok ? f.off[i] + kofs : 0;
+                cp_async16(raw + i * (PROD_T * 16), x + o, ok);
+                if (MODE == XM_DY) cp_async16(raw2 + i * (PROD_T * 16), x2 + o, ok);
             }
+        }
+    }
+    // K-major: fetch the transform parameters of k-block kb (call early: the latency hides behind the waits)
+    __device__ __forceinline__ void load_params(int kb) {
+        if (LAY == TCG_LAY_KM && MODE != XM_PLAIN) {
+            int ch = kb * E::KE + gc * E::EPV;
+            ch = min(ch, R - (E::TF32 ? 4 : 8));          // columns beyond R meet zero-filled B columns: any finite value does
+            xf_load<MODE>(vt, ch, par);
+            if (!E::TF32) xf_load<MODE>(vt, ch + 4, par2);
         }
     }
     // transform the raw pieces and store them into the operand tile (hi [, lo])
-    template <int NP>
-    __device__ __forceinline__ void convert(int kb, int mn0, int np, uint32_t raw, uint32_t raw2, uint32_t op_hi, uint32_t op_lo) {
-        const int gi = geom(kb);
-        if (LAY == TCG_LAY_KM && MODE != XM_PLAIN && kb != cached_kb) {
-            const int ch = kb * E::KE + gc(gi) * E::EPV;
-            if (ch + E::EPV <= R) {
-                xf_load<MODE>(vt, ch, par);
-                if (!E::TF32) xf_load<MODE>(vt, ch + 4, par2);
-            }
-            cached_kb = kb;
-        }
+    __device__ __forceinline__ void convert(int kb, const CTile& c, uint32_t raw, uint32_t raw2, uint32_t op_hi, uint32_t op_lo) {
+        if (!active(kb)) return;
+        const bool kok = kb_ok(kb);
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
             if (i < np) {
-                size_t boff; int ch;
-                const bool ok = src(kb, mn0, i, gi, boff, ch);
-                const uint32_t so = gsoff(gi) + i * gsstep(gi);
+                const uint32_t so = soff + i * 8192;
                 float4 r = lds4(raw + i * (PROD_T * 16)), r2 = f4zero();
                 if (MODE == XM_DY) r2 = lds4(raw2 + i * (PROD_T * 16));
-                if (LAY == TCG_LAY_MM && MODE != XM_PLAIN && ok) {
+                // zero-filled raw data stays zero only for PLAIN; transformed operands must be masked where the
+                // OTHER operand is not guaranteed to be zero: MN-major reduction rows / columns beyond the tensor
+                bool ok = true;
+                if (LAY == TCG_LAY_MM && MODE != XM_PLAIN) {
+                    ok = kok && ((c.ok >> i) & 1u);
+                    int ch = c.ch0 + ASTEP * MNA * i;
+                    ch = min(ch, mn_ext - (E::TF32 ? 4 : 8));
                     xf_load<MODE>(vt, ch, par);
                     if (!E::TF32) xf_load<MODE>(vt, ch + 4, par2);
                 }
@@ -308,7 +326,6 @@ struct OpLoader {
             }
         }
     }
-    XfP par2;
 };
 
 // =====================================================================================================
@@ -351,23 +368,39 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
     if (warp > MMA_WARP) {
         // ======================================= PRODUCERS =======================================
         const int pt = tid - (EPI_T + MMA_T);
-        constexpr int NPB = E::TF32 ? 4 : 8;
-        OpLoader<T, ALAY, AMODE> LA;
-        OpLoader<T, BLAY, BMODE> LB;
-        LA.init(g.a, g.lda, g.P, g.R, g.nkb, g.ac_last, pt);
-        LB.init(g.b, g.ldb, g.Q, g.R, g.nkb, g.ac_last, pt);
+        constexpr int NPB = (E::TF32 ? 1024 : 2048) / PROD_T;
+        typedef OpLoader<T, ALAY, AMODE, APT> LoaderA;
+        typedef OpLoader<T, BLAY, BMODE, NPB> LoaderB;
+        LoaderA LA;
+        LoaderB LB;
+        LA.init(g.a, g.lda, g.P, g.R, g.nkb, g.ac_last, pt, BM);
+        LB.init(g.b, g.ldb, g.Q, g.R, g.nkb, g.ac_last, pt, g.BN);
         const uint32_t raw0 = s_base + g.off_raw + pt * 16;
-        constexpr int slotA2 = 4, slotB = AMODE == XM_DY ? 8 : 4;
+        constexpr int slotA2 = APT, slotB = AMODE == XM_DY ? 2 * APT : APT;
+        typename LoaderA::FTile fa;
+        typename LoaderA::CTile ca;
+        typename LoaderB::FTile fb;
+        typename LoaderB::CTile cb;
         if (g.b_res) {
-            // weights: convert every k-block once, keep them resident for all of this CTA's tiles
-            for (int kb = 0; kb < g.nkb; ++kb) {
-                const int np = LB.count(LB.geom(kb), g.BN);
-                const uint32_t b_hi = s_base + g.off_bres + kb * (E::NM * g.b_op_bytes), b_lo = b_hi + g.b_op_bytes;
-                LB.template issue<NPB>(kb, 0, np, raw0, 0);
+            // weights: convert every k-block once, keep them resident for all of this CTA's tiles.  The raw
+            // staging slots of the A ring double as a software pipeline so the loads of n_raw k-blocks overlap.
+            LB.begin(fb, 0);
+            LB.begin(cb, 0);
+            for (int d = 0; d < g.n_raw; ++d) {
+                if (d < g.nkb) LB.issue(d, fb, raw0 + d * g.raw_stage_bytes, 0);
                 cp_async_commit();
-                cp_async_wait<0>();
-                LB.template convert<NPB>(kb, 0, np, raw0, 0, b_hi, b_lo);
             }
+            int rsb = 0;
+            for (int kb = 0; kb < g.nkb; ++kb) {
+                if (g.n_raw == 4) cp_async_wait<3>(); else if (g.n_raw == 3) cp_async_wait<2>(); else cp_async_wait<1>();
+                const uint32_t b_hi = s_base + g.off_bres + kb * (E::NM * g.b_op_bytes), b_lo = b_hi + g.b_op_bytes;
+                LB.load_params(kb);
+                LB.convert(kb, cb, raw0 + rsb * g.raw_stage_bytes, 0, b_hi, b_lo);
+                if (kb + g.n_raw < g.nkb) LB.issue(kb + g.n_raw, fb, raw0 + rsb * g.raw_stage_bytes, 0);
+                cp_async_commit();
+                if (++rsb == g.n_raw) rsb = 0;
+            }
+            cp_async_wait<0>();
             tc::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(bfull);
@@ -375,11 +408,17 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
         KIter fetch, cons;
         fetch.init(g, blockIdx.x, total, gridDim.x);
         cons.init(g, blockIdx.x, total, gridDim.x);
+        int f_it = -1, c_it = -1;                  // work item whose tile state fa/fb (ca/cb) currently describes
 
         auto issue = [&](const KIter& k, int rs) {
+            if (k.it != f_it) {
+                LA.begin(fa, k.w.p0);
+                if (!g.b_res) LB.begin(fb, k.w.q0);
+                f_it = k.it;
+            }
             const uint32_t rbase = raw0 + rs * g.raw_stage_bytes;
-            LA.template issue<4>(k.kb, k.w.p0, LA.count(LA.geom(k.kb), BM), rbase, rbase + slotA2 * (PROD_T * 16));
-            if (!g.b_res) LB.template issue<NPB>(k.kb, k.w.q0, LB.count(LB.geom(k.kb), g.BN), rbase + slotB * (PROD_T * 16), 0);
+            LA.issue(k.kb, fa, rbase, rbase + slotA2 * (PROD_T * 16));
+            if (!g.b_res) LB.issue(k.kb, fb, rbase + slotB * (PROD_T * 16), 0);
         };
 
         for (int d = 0; d < g.n_raw; ++d) {
@@ -389,14 +428,20 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
         int rs = 0, os = 0;
         uint32_t par = 1;
         while (cons.valid()) {
+            if (cons.it != c_it) {
+                LA.begin(ca, cons.w.p0);
+                if (!g.b_res) LB.begin(cb, cons.w.q0);
+                c_it = cons.it;
+            }
+            LA.load_params(cons.kb);               // issued before the waits: their latency is hidden
+            if (!g.b_res) LB.load_params(cons.kb);
             if (g.n_raw == 4) cp_async_wait<3>(); else if (g.n_raw == 3) cp_async_wait<2>(); else cp_async_wait<1>();
             mbar_wait_guard(&empty[os], par, g.wait_mode);
             const uint32_t rbase = raw0 + rs * g.raw_stage_bytes;
             const uint32_t a_hi = s_base + os * g.op_stage_bytes, a_lo = a_hi + g.a_op_bytes;
             const uint32_t b_hi = a_hi + b_in_stage, b_lo = b_hi + g.b_op_bytes;
-            LA.template convert<4>(cons.kb, cons.w.p0, LA.count(LA.geom(cons.kb), BM), rbase, rbase + slotA2 * (PROD_T * 16), a_hi, a_lo);
-            if (!g.b_res)
-                LB.template convert<NPB>(cons.kb, cons.w.q0, LB.count(LB.geom(cons.kb), g.BN), rbase + slotB * (PROD_T * 16), 0, b_hi, b_lo);
+            LA.convert(cons.kb, ca, rbase, rbase + slotA2 * (PROD_T * 16), a_hi, a_lo);
+            if (!g.b_res) LB.convert(cons.kb, cb, rbase + slotB * (PROD_T * 16), 0, b_hi, b_lo);
             tc::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&full[os]);
@@ -473,7 +518,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
         float* outF = reinterpret_cast<float*>(g.out);
         const int nchunks = (g.BN + 31) >> 5;
         int last_chunk = -1;                            // last chunk this warp reads from TMEM
-        for (int c = half; c < nchunks; c += 2) last_chunk = c;
+        for (int c = half; c < nchunks; c += EPI_SETS) last_chunk = c;
         int ni = 0;
         int cur_q0 = -1;
         auto flush = [&](int q0) {
@@ -507,7 +552,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&tempty[acc]);
             }
-            for (int ci = half; ci < nchunks; ci += 2) {
+            for (int ci = half; ci < nchunks; ci += EPI_SETS) {
                 const int c0 = ci * 32;
                 const int ncol = min(32, g.BN - c0);
                 uint32_t r[32];
@@ -543,43 +588,59 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
                 }
                 float4 ls = f4zero(), lq4 = f4zero();
                 const int row_base = w.p0 + lq * 32 + rs;
+                // rows are handled in two batches of four so that the global loads of the dgrad epilogue (saved conv
+                // output y for the activation mask / BN reductions, skip gradient) are all in flight together
+                // instead of one dependent round trip per row
 #pragma unroll
-                for (int ps = 0; ps < 8; ++ps) {
-                    const int trow = ps * 4 + rs;
-                    const int row = row_base + ps * 4;
-                    if (!(cok && row < g.P)) continue;
-                    float4 v = lds4(stg_u + (trow * STG_LD + 4 * cq) * 4);
-                    const size_t off = (size_t)row * g.Q + col;
-                    if (EPI == TCG_EPI_FWD) {
-                        if (!plain_out) {
-                            v.x = act_fwd(v.x + bias4.x, oact); v.y = act_fwd(v.y + bias4.y, oact);
-                            v.z = act_fwd(v.z + bias4.z, oact); v.w = act_fwd(v.w + bias4.w, oact);
+                for (int hb = 0; hb < 2; ++hb) {
+                    float4 yv[4], sv[4];
+                    if (EPI == TCG_EPI_DGRAD) {
+#pragma unroll
+                        for (int p4 = 0; p4 < 4; ++p4) {
+                            const int row = row_base + (hb * 4 + p4) * 4;
+                            const bool ok = cok && row < g.P;
+                            const size_t off = (size_t)row * g.Q + col;
+                            yv[p4] = (g.has_bnb && ok) ? Vec4<T>::ld(reinterpret_cast<const T*>(g.bnb.y) + off) : f4zero();
+                            sv[p4] = (g.skip && ok) ? Vec4<T>::ld(reinterpret_cast<const T*>(g.skip) + off) : f4zero();
                         }
-                        Vec4<T>::st(outT + off, v);
-                        if (!E::TF32) {      // statistics of the value as stored (bf16-rounded)
-                            v.x = __bfloat162float(__float2bfloat16_rn(v.x)); v.y = __bfloat162float(__float2bfloat16_rn(v.y));
-                            v.z = __bfloat162float(__float2bfloat16_rn(v.z)); v.w = __bfloat162float(__float2bfloat16_rn(v.w));
-                        }
-                        ls.x += v.x; ls.y += v.y; ls.z += v.z; ls.w += v.w;
-                        lq4.x = fmaf(v.x, v.x, lq4.x); lq4.y = fmaf(v.y, v.y, lq4.y); lq4.z = fmaf(v.z, v.z, lq4.z); lq4.w = fmaf(v.w, v.w, lq4.w);
-                    } else if (EPI == TCG_EPI_DGRAD) {
-                        v.x *= g.scale_out; v.y *= g.scale_out; v.z *= g.scale_out; v.w *= g.scale_out;
-                        if (g.skip) {
-                            const float4 s = Vec4<T>::ld(reinterpret_cast<const T*>(g.skip) + off);
-                            v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
-                        }
-                        if (g.has_bnb) {
-                            const float4 y = Vec4<T>::ld(reinterpret_cast<const T*>(g.bnb.y) + off);
-                            v.x *= act_bwd(fmaf(y.x, sc4.x, sh4.x), oact); v.y *= act_bwd(fmaf(y.y, sc4.y, sh4.y), oact);
-                            v.z *= act_bwd(fmaf(y.z, sc4.z, sh4.z), oact); v.w *= act_bwd(fmaf(y.w, sc4.w, sh4.w), oact);
+                    }
+#pragma unroll
+                    for (int p4 = 0; p4 < 4; ++p4) {
+                        const int ps = hb * 4 + p4;
+                        const int trow = ps * 4 + rs;
+                        const int row = row_base + ps * 4;
+                        if (!(cok && row < g.P)) continue;
+                        float4 v = lds4(stg_u + (trow * STG_LD + 4 * cq) * 4);
+                        const size_t off = (size_t)row * g.Q + col;
+                        if (EPI == TCG_EPI_FWD) {
+                            if (!plain_out) {
+                                v.x = act_fwd(v.x + bias4.x, oact); v.y = act_fwd(v.y + bias4.y, oact);
+                                v.z = act_fwd(v.z + bias4.z, oact); v.w = act_fwd(v.w + bias4.w, oact);
+                            }
+                            Vec4<T>::st(outT + off, v);
+                            if (!E::TF32) {      // statistics of the value as stored (bf16-rounded)
+                                v.x = __bfloat162float(__float2bfloat16_rn(v.x)); v.y = __bfloat162float(__float2bfloat16_rn(v.y));
+                                v.z = __bfloat162float(__float2bfloat16_rn(v.z)); v.w = __bfloat162float(__float2bfloat16_rn(v.w));
+                            }
                             ls.x += v.x; ls.y += v.y; ls.z += v.z; ls.w += v.w;
-                            lq4.x = fmaf(v.x, (y.x - mu4.x) * rs4.x, lq4.x); lq4.y = fmaf(v.y, (y.y - mu4.y) * rs4.y, lq4.y);
-                            lq4.z = fmaf(v.z, (y.z - mu4.z) * rs4.z, lq4.z); lq4.w = fmaf(v.w, (y.w - mu4.w) * rs4.w, lq4.w);
+                            lq4.x = fmaf(v.x, v.x, lq4.x); lq4.y = fmaf(v.y, v.y, lq4.y); lq4.z = fmaf(v.z, v.z, lq4.z); lq4.w = fmaf(v.w, v.w, lq4.w);
+                        } else if (EPI == TCG_EPI_DGRAD) {
+                            v.x *= g.scale_out; v.y *= g.scale_out; v.z *= g.scale_out; v.w *= g.scale_out;
+                            const float4 sk = sv[p4];
+                            v.x += sk.x; v.y += sk.y; v.z += sk.z; v.w += sk.w;
+                            if (g.has_bnb) {
+                                const float4 y = yv[p4];
+                                v.x *= act_bwd(fmaf(y.x, sc4.x, sh4.x), oact); v.y *= act_bwd(fmaf(y.y, sc4.y, sh4.y), oact);
+                                v.z *= act_bwd(fmaf(y.z, sc4.z, sh4.z), oact); v.w *= act_bwd(fmaf(y.w, sc4.w, sh4.w), oact);
+                                ls.x += v.x; ls.y += v.y; ls.z += v.z; ls.w += v.w;
+                                lq4.x = fmaf(v.x, (y.x - mu4.x) * rs4.x, lq4.x); lq4.y = fmaf(v.y, (y.y - mu4.y) * rs4.y, lq4.y);
+                                lq4.z = fmaf(v.z, (y.z - mu4.z) * rs4.z, lq4.z); lq4.w = fmaf(v.w, (y.w - mu4.w) * rs4.w, lq4.w);
+                            }
+                            Vec4<T>::st(outT + off, v);
+                        } else {
+                            atomicAdd(outF + off, v.x); atomicAdd(outF + off + 1, v.y);
+                            atomicAdd(outF + off + 2, v.z); atomicAdd(outF + off + 3, v.w);
                         }
-                        Vec4<T>::st(outT + off, v);
-                    } else {
-                        atomicAdd(outF + off, v.x); atomicAdd(outF + off + 1, v.y);
-                        atomicAdd(outF + off + 2, v.z); atomicAdd(outF + off + 3, v.w);
                     }
                 }
                 if (do_stats) {
@@ -673,7 +734,7 @@ int launch_cfg(TcgArgs& a, cudaStream_t st) {
         const uint32_t bres_bytes = (uint32_t)a.nkb * E::NM * a.b_op_bytes;
         a.b_res = (EPI != TCG_EPI_ATOMIC && numQt == 1 && BMODE == XM_PLAIN && bres_bytes <= BRES_LIMIT) ? 1 : 0;
         a.op_stage_bytes = E::NM * (a.a_op_bytes + (a.b_res ? 0 : a.b_op_bytes));
-        a.raw_stage_bytes = (4 + (AMODE == XM_DY ? 4 : 0) + (a.b_res ? 0 : a.nb_slots)) * PROD_T * 16;
+        a.raw_stage_bytes = (APT + (AMODE == XM_DY ? APT : 0) + (a.b_res ? 0 : a.nb_slots)) * PROD_T * 16;
         const uint32_t fixed = EPI_W * 32 * STG_LD * 4 + EPI_W * 2 * BN * 4 + 256 + (a.b_res ? bres_bytes : 0);
         a.n_op = 2;
         a.n_raw = 0;
