@@ -221,6 +221,41 @@ int b200sp_style_embed(const float *noise, const float *A, const float *mean, co
 /* out[b][t] = sum_d emb[b][d] W[t][d] + bias[t]: the 26 Linear(100->C) of ghiasi.py:50-51,87-90 concatenated */
 int b200sp_style_linear(const float *emb, const float *W, const float *bias, float *out, int B, int D, int T, void *stream);
 
+/* ---- SPN / AlexNet path (src/nets/spn.py:37-143, src/core/trainer.py:114-199), NHWC fp32 ------------------- */
+/* Strided GEMMs (tensor-core path only): a grouped convolution (spn.py:65,73,76) is one GEMM per group over a
+ * column slice of the activation.  fwd: Y[M,N] (row stride ldy) = act(X[M,K] (row stride ldx) W[N,K]^T + bias);
+ * dgrad: G[M,K] = dY[M,N] (row stride lddy) W[N,K] (+skip) then the activation mask of bn->y (scale/shift/s1 NULL);
+ * wgrad: dW[N,K] += dY[M,N]^T X[M,K]. */
+int b200sp_gemm_fwd(const b200sp_vtensor *x, int ldx, const float *w, const float *bias, int out_act, void *y, int ldy,
+                    int M, int N, int K, int dtype, void *stream);
+int b200sp_gemm_dgrad(const b200sp_vtensor *dy, int lddy, const float *w, const void *skip, float scale_out, void *g,
+                      const b200sp_bnbwd *bn, int M, int N, int K, int dtype, void *stream);
+int b200sp_gemm_wgrad(const b200sp_vtensor *dy, int lddy, const b200sp_vtensor *x, int ldx, float *dw,
+                      int M, int N, int K, int dtype, void *stream);
+int b200sp_colsum_f32(const b200sp_vtensor *dy, float *out /* += */, int M, int N, int dtype, void *stream);
+/* patch matrix of a k x k / stride / zero-pad convolution over channels [c_off, c_off+Cg) of x ([B,H,W,C] NHWC, or the
+ * loader's NCHW image when nchw != 0): col[B*Ho*Wo][Kp], column (kh*k+kw)*Cg + c, zero-padded to Kp columns */
+int b200sp_im2col(const float *x, float *col, int B, int H, int W, int C, int c_off, int Cg, int k, int stride, int pad,
+                  int Kp, int nchw, void *stream);
+/* adjoint of im2col (gather form), times the ReLU mask of act_mask (same layout as dx) when given */
+int b200sp_col2im(const float *dcol, float *dx, const float *act_mask, int B, int H, int W, int C, int c_off, int Cg, int k,
+                  int stride, int pad, int Kp, void *stream);
+/* MaxPool2d(3,2) [+ LocalResponseNorm(size 2, alpha, beta, k=1)] (spn.py:61-62,66-67,77); pooled (may be NULL) keeps the
+ * pre-LRN values for the backward */
+int b200sp_pool_lrn_fwd(const float *x, float *pooled, float *out, int B, int H, int W, int C, int lrn, float alpha, float beta,
+                        void *stream);
+int b200sp_pool_lrn_bwd(const float *g_out, const float *pooled, const float *x, float *scratch, float *dx, int B, int H, int W,
+                        int C, int lrn, float alpha, float beta, int relu_mask, void *stream);
+/* Dropout(p) (spn.py:81,85,92,96): counter-based mask from `seed` (not torch's RNG stream); mask saved for backward */
+int b200sp_dropout_fwd(const float *x, float *out, uint8_t *mask, int64_t n, float p, uint64_t seed, void *stream);
+int b200sp_dropout_bwd(float *g, const uint8_t *mask, int64_t n, float p, void *stream);
+/* softmax_cross_entropy_with_logits (spn.py:37-48): loss_rows[b] = -sum_j t_bj log_softmax(z_b)_j;
+ * dlogits (may be NULL) = weight/B * (softmax * sum_j t - t)  (weight: 1 for the class branch, 10 for the regress branch) */
+int b200sp_soft_ce(const float *logits, const float *target, float *loss_rows, float *dlogits, int B, int N, float weight,
+                   void *stream);
+int b200sp_soft_ce_mean(const float *rows_c, const float *rows_r, float *loss2, int B, void *stream);
+int b200sp_relu_mask(float *g, const float *a, int64_t n, void *stream);
+
 /* ---- DANN domain classifier tail + loss (revgrad.py:75-80 AvgPool2d(7) -> Conv2d(1280,1,1); dann.py:85-92
  * binary_cross_entropy_with_logits(mean) against a constant label).  The first conv (+bias+ReLU) is
  * b200sp_pw_fwd.  h is [B,HW,C] NHWC. */

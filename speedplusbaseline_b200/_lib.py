@@ -101,6 +101,19 @@ _SIGS = {
     'b200sp_in_apply_final': ([vp, vp, vp, vp, i32, i32, i32, i32, i32, vp], i32),
     'b200sp_style_embed': ([vp, vp, vp, vp, f32, vp, i32, i32, vp], i32),
     'b200sp_style_linear': ([vp, vp, vp, vp, i32, i32, i32, vp], i32),
+    'b200sp_gemm_fwd': ([PVT, i32, vp, vp, i32, vp, i32, i32, i32, i32, i32, vp], i32),
+    'b200sp_gemm_dgrad': ([PVT, i32, vp, vp, f32, vp, PBB, i32, i32, i32, i32, vp], i32),
+    'b200sp_gemm_wgrad': ([PVT, i32, PVT, i32, vp, i32, i32, i32, i32, vp], i32),
+    'b200sp_colsum_f32': ([PVT, vp, i32, i32, i32, vp], i32),
+    'b200sp_im2col': ([vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp], i32),
+    'b200sp_col2im': ([vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp], i32),
+    'b200sp_pool_lrn_fwd': ([vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp], i32),
+    'b200sp_pool_lrn_bwd': ([vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, i32, vp], i32),
+    'b200sp_dropout_fwd': ([vp, vp, vp, i64, f32, C.c_uint64, vp], i32),
+    'b200sp_dropout_bwd': ([vp, vp, i64, f32, vp], i32),
+    'b200sp_soft_ce': ([vp, vp, vp, vp, i32, i32, f32, vp], i32),
+    'b200sp_soft_ce_mean': ([vp, vp, vp, i32, vp], i32),
+    'b200sp_relu_mask': ([vp, vp, i64, vp], i32),
     'b200sp_dann_head_fwd': ([vp, vp, vp, vp, vp, i32, i32, i32, i32, vp], i32),
     'b200sp_bce_logits': ([vp, f32, vp, vp, vp, i32, vp], i32),
     'b200sp_dann_head_bwd': ([vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp], i32),

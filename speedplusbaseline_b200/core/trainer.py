@@ -137,3 +137,108 @@ def train_single_epoch_krn(epoch, cfg, model, data_loader, optimizer,
     if writer is not None:
         writer.add_scalar('train/loss_x', loss_x_meter.avg, epoch)
         writer.add_scalar('train/loss_y', loss_y_meter.avg, epoch)
+
+
+class SPNTrainStep:
+    """One fused SPN training iteration (reference trainer.py:137-186): forward, CE(class) + 10 CE(weights),
+    backward, clip_grad_value_(1.0) + AdamW (one launch, optim.FusedAdamW clip_mode=2).
+    step(images [B,3,227,227], yClasses [B,N], yWeights [B,N]) -> device tensor (loss_class, loss_regress)."""
+
+    def __init__(self, model, optimizer, use_graph=True, world_size=1, process_group=None):
+        self.model, self.opt, self.use_graph = model, optimizer, use_graph
+        self.world, self.pg = world_size, process_group
+        self.sync = GradSync(world_size, process_group)
+        if world_size > 1:
+            optimizer.grad_scale = self.sync.grad_scale
+        self._graphs = self._static = self._sig = None
+        self._step = 0
+
+    def _fwd_bwd(self, images, yc, yw):
+        eng = self.model.engine
+        eng.store.grads.zero_()
+        eng.forward(images, yc, yw, train=True)
+        eng.backward()
+        return eng.loss2
+
+    def eager(self, images, yc, yw):
+        self.opt.sync_hyperparams()
+        self.model.engine.step_seed = self._step
+        self._step += 1
+        out = self._fwd_bwd(images, yc, yw)
+        self.sync.allreduce(self.model.engine.store.grads)
+        self.opt.step(sync=False)
+        return out
+
+    def step(self, images, yc, yw):
+        # dropout masks are seeded per step from the host, so the step is replayed eagerly unless dropout is off
+        # (a captured graph would freeze the seed); the launch count is ~110, all asynchronous.
+        if not self.use_graph or self.model.engine.drop_p > 0:
+            return self.eager(images, yc, yw)
+        sig = tuple(tuple(t.shape) for t in (images, yc, yw))
+        if self._graphs is None or sig != self._sig:
+            self._static = tuple(torch.empty_like(t) for t in (images, yc, yw))
+            for s, t in zip(self._static, (images, yc, yw)):
+                s.copy_(t)
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._fwd_bwd(*self._static)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                self._fwd_bwd(*self._static)
+            with torch.cuda.graph(g2):
+                self.opt.step(sync=False)
+            self._graphs, self._sig = (g1, g2), sig
+        self.opt.sync_hyperparams()
+        for s, t in zip(self._static, (images, yc, yw)):
+            s.copy_(t, non_blocking=True)
+        self._graphs[0].replay()
+        self.sync.allreduce(self.model.engine.store.grads)
+        self._graphs[1].replay()
+        return self.model.engine.loss2
+
+
+def train_single_epoch_spn(epoch, cfg, model, data_loader, optimizer,
+                           writer, device, styleAugmentor=None, scaler=None):
+    """Same signature and behaviour as reference trainer.py:114-199."""
+    training_time_meter = AverageMeter('ms')
+    loss_class_meter = AverageMeter('-')
+    loss_weight_meter = AverageMeter('-')
+    model.train()
+    for pg in optimizer.param_groups:
+        lr = pg['lr']
+    stepper = getattr(model, '_train_step', None)
+    if stepper is None or stepper.opt is not optimizer:
+        stepper = SPNTrainStep(model, optimizer, use_graph=getattr(cfg, 'use_graph', True))
+        model._train_step = stepper
+    pending = None
+    for idx, (images, yClasses, yWeights) in enumerate(data_loader):
+        start = time.time()
+        B = images.shape[0]
+        images = images.to(device, non_blocking=True).float().contiguous()
+        yClasses = yClasses.to(device, non_blocking=True).float().contiguous()
+        yWeights = yWeights.to(device, non_blocking=True).float().contiguous()
+        if styleAugmentor is not None and random.random() < cfg.texture_ratio:
+            images = styleAugmentor(images)
+        loss2 = stepper.step(images, yClasses, yWeights)
+        if pending is not None:
+            hl, pb, pev = pending
+            pev.synchronize()
+            loss_class_meter.update(float(hl[0]), pb)
+            loss_weight_meter.update(float(hl[1]), pb)
+        host = torch.empty(2, pin_memory=True)
+        host.copy_(loss2, non_blocking=True)
+        ev = torch.cuda.Event(); ev.record()
+        pending = (host, B, ev)
+        training_time_meter.update((time.time() - start) * 1000, B)
+        report_progress(epoch=epoch, lr=lr, epoch_iter=idx + 1, epoch_size=len(data_loader),
+                        time=training_time_meter, is_train=True, loss_c=loss_class_meter, loss_r=loss_weight_meter)
+    if pending is not None:
+        torch.cuda.synchronize()
+        loss_class_meter.update(float(pending[0][0]), pending[1])
+        loss_weight_meter.update(float(pending[0][1]), pending[1])
+    if writer is not None:
+        writer.add_scalar('train/loss_c', loss_class_meter.avg, epoch)
+        writer.add_scalar('train/loss_r', loss_weight_meter.avg, epoch)

@@ -396,3 +396,35 @@ extern "C" int b200sp_pw_wgrad(const b200sp_vtensor* dy, const b200sp_vtensor* x
     if (dbias) return b200sp_colsum_f32(dy, dbias, M, N, dtype, stream);
     return 0;
 }
+
+// ---- strided variants (grouped convolutions as per-group GEMMs over column slices; SPN, src/nets/spn.py:65,73,76) ----
+// tensor-core path only: every extent must satisfy the 16-byte granularity rules of tcgemm_launch.
+extern "C" int b200sp_gemm_fwd(const b200sp_vtensor* x, int ldx, const float* w, const float* bias, int out_act, void* y, int ldy,
+                               int M, int N, int K, int dtype, void* stream) {
+    if (!x || x->mode == B200SP_VT_DY || dtype != B200SP_F32) return B200SP_EINVAL;
+    TcgProblem p = {};
+    p.a = *x; p.b = plain_vt(w); p.a_lay = TCG_LAY_KM; p.b_lay = TCG_LAY_KM;
+    p.P = M; p.Q = N; p.R = K; p.lda = ldx; p.ldb = K; p.ldo = ldy; p.epi = TCG_EPI_FWD; p.dtype = dtype;
+    p.out = y; p.bias = bias; p.out_act = out_act; p.bnf = nullptr; p.count = (double)M;
+    return tcgemm_launch(p, (cudaStream_t)stream);
+}
+
+extern "C" int b200sp_gemm_dgrad(const b200sp_vtensor* dy, int lddy, const float* w, const void* skip, float scale_out, void* g,
+                                 const b200sp_bnbwd* bn, int M, int N, int K, int dtype, void* stream) {
+    if (!dy || dtype != B200SP_F32) return B200SP_EINVAL;
+    TcgProblem p = {};
+    p.a = *dy; p.b = plain_vt(w); p.a_lay = TCG_LAY_KM; p.b_lay = TCG_LAY_MM;
+    p.P = M; p.Q = K; p.R = N; p.lda = lddy; p.ldb = K; p.epi = TCG_EPI_DGRAD; p.dtype = dtype;
+    p.out = g; p.skip = skip; p.scale_out = scale_out; p.bnb = bn; p.count = (double)M;
+    return tcgemm_launch(p, (cudaStream_t)stream);
+}
+
+extern "C" int b200sp_gemm_wgrad(const b200sp_vtensor* dy, int lddy, const b200sp_vtensor* x, int ldx, float* dw,
+                                 int M, int N, int K, int dtype, void* stream) {
+    if (!dy || !x || x->mode == B200SP_VT_DY || dtype != B200SP_F32) return B200SP_EINVAL;
+    TcgProblem p = {};
+    p.a = *dy; p.b = *x; p.a_lay = TCG_LAY_MM; p.b_lay = TCG_LAY_MM;
+    p.P = N; p.Q = K; p.R = M; p.lda = lddy; p.ldb = ldx; p.epi = TCG_EPI_ATOMIC; p.dtype = dtype;
+    p.out = dw;
+    return tcgemm_launch(p, (cudaStream_t)stream);
+}

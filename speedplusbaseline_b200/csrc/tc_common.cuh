@@ -164,12 +164,15 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int c) { return (uint32_t)(
 // (32-byte chunks XORed with row & 3; 4-row groups are 512 B apart = SBO)
 __device__ __forceinline__ uint32_t sw128b32_off(int r, int c) { return (uint32_t)(r * 128 + ((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4))); }
 
-// fp32 -> (tf32 hi, fp32 residual lo): hi+lo == v exactly; the tensor core drops lo's low 13 bits (error 2^-22 |v|)
+// fp32 -> (tf32 hi, tf32 lo):  hi = rn(v), lo = rn(v - hi).  lo is ROUNDED to tf32 here: the tensor core would
+// otherwise truncate its low 13 bits, a biased error of ~2^-21 |v| per operand that accumulates linearly over K;
+// rounded, the residual error is unbiased and ~2^-23 |v|.
 __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
-    uint32_t h;
+    uint32_t h, l;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
     hi = __uint_as_float(h);
-    lo = v - hi;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
+    lo = __uint_as_float(l);
 }
 
 }  // namespace tc

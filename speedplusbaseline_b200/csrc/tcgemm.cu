@@ -41,7 +41,7 @@ template <> struct ET<bf16>  { static constexpr int ES = 2, KE = 64, EPV = 8, NM
 
 struct TcgArgs {
     b200sp_vtensor a, b;
-    int P, Q, R, lda, ldb;
+    int P, Q, R, lda, ldb, ldo;
     int BN, numPt, numQt, splits, kb_per_split, nkb;
     int n_op, n_raw;
     int nb_pieces, nb_slots;         // B pieces per k-block; per-thread B slots = ceil(nb_pieces / PROD_T)
@@ -599,7 +599,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
                         for (int p4 = 0; p4 < 4; ++p4) {
                             const int row = row_base + (hb * 4 + p4) * 4;
                             const bool ok = cok && row < g.P;
-                            const size_t off = (size_t)row * g.Q + col;
+                            const size_t off = (size_t)row * g.ldo + col;
                             yv[p4] = (g.has_bnb && ok) ? Vec4<T>::ld(reinterpret_cast<const T*>(g.bnb.y) + off) : f4zero();
                             sv[p4] = (g.skip && ok) ? Vec4<T>::ld(reinterpret_cast<const T*>(g.skip) + off) : f4zero();
                         }
@@ -611,7 +611,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
                         const int row = row_base + ps * 4;
                         if (!(cok && row < g.P)) continue;
                         float4 v = lds4(stg_u + (trow * STG_LD + 4 * cq) * 4);
-                        const size_t off = (size_t)row * g.Q + col;
+                        const size_t off = (size_t)row * g.ldo + col;
                         if (EPI == TCG_EPI_FWD) {
                             if (!plain_out) {
                                 v.x = act_fwd(v.x + bias4.x, oact); v.y = act_fwd(v.y + bias4.y, oact);
@@ -808,6 +808,8 @@ int tcgemm_launch(const TcgProblem& p, cudaStream_t st) {
     TcgArgs a = {};
     a.a = p.a; a.b = p.b;
     a.P = p.P; a.Q = p.Q; a.R = p.R; a.lda = p.lda; a.ldb = p.ldb;
+    a.ldo = p.ldo > 0 ? p.ldo : p.Q;
+    if (a.ldo % 4) return B200SP_ENOSYS;
     a.a_dy = p.a.mode == B200SP_VT_DY;
     a.out = p.out; a.bias = p.bias; a.out_act = p.out_act;
     a.has_bnf = p.bnf != nullptr;

@@ -13,6 +13,7 @@ struct TcgProblem {
     int a_lay, b_lay;
     int P, Q, R;
     int lda, ldb;
+    int ldo;                   // row stride of `out` (FWD / DGRAD); 0 => Q
     int epi;
     int dtype;                 // B200SP_F32 (3xTF32 math) | B200SP_BF16
     void* out;                 // [P,Q] T (FWD, DGRAD) or float (ATOMIC, accumulated)

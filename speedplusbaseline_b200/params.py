@@ -25,11 +25,18 @@ class Entry:
 
     def __init__(self, key, kind, ref_shape):
         self.key, self.kind, self.ref_shape = key, kind, tuple(ref_shape)
-        n = 1
-        for s in ref_shape:
-            n *= s
-        self.numel = n
+        self.numel = native_numel(kind, self.ref_shape)      # elements in the kernel-native layout
         self.off = -1
+
+
+def native_numel(kind, ref_shape):
+    n = 1
+    for s in ref_shape:
+        n *= s
+    if kind == 'ohwi_pad4':                # rows padded to a multiple of 4 (16-byte GEMM granularity)
+        k = n // ref_shape[0]
+        return ref_shape[0] * _align4(k)
+    return n
 
 
 def to_native(kind, t):
@@ -37,6 +44,15 @@ def to_native(kind, t):
         return t.reshape(t.shape[0], 9).t().contiguous()
     if kind == 'ohwi':                     # [O,I,kh,kw] -> [O][kh][kw][I]
         return t.permute(0, 2, 3, 1).contiguous()
+    if kind == 'ohwi_pad4':                # same, each row zero-padded to a multiple of 4 (SPN conv1: 363 -> 364)
+        O = t.shape[0]
+        r = t.permute(0, 2, 3, 1).reshape(O, -1)
+        out = t.new_zeros(O, _align4(r.shape[1]))
+        out[:, :r.shape[1]] = r
+        return out
+    if kind.startswith('fc_chw'):          # Linear over a flattened NCHW map -> columns in NHWC order (SPN fc6/fc9)
+        c, h, w = (int(v) for v in kind.split(':')[1].split('x'))
+        return t.reshape(t.shape[0], c, h, w).permute(0, 2, 3, 1).reshape(t.shape[0], -1).contiguous()
     return t.contiguous()
 
 
@@ -47,6 +63,12 @@ def from_native(kind, flat, ref_shape):
     if kind == 'ohwi':
         O, I, kh, kw = ref_shape
         return flat.view(O, kh, kw, I).permute(0, 3, 1, 2).contiguous()
+    if kind == 'ohwi_pad4':
+        O, I, kh, kw = ref_shape
+        return flat.view(O, -1)[:, :I * kh * kw].reshape(O, kh, kw, I).permute(0, 3, 1, 2).contiguous()
+    if kind.startswith('fc_chw'):
+        c, h, w = (int(v) for v in kind.split(':')[1].split('x'))
+        return flat.view(ref_shape[0], h, w, c).permute(0, 3, 1, 2).reshape(ref_shape).contiguous()
     return flat.view(ref_shape).clone()
 
 
