@@ -122,6 +122,69 @@ def cpu_baseline(steps_n=3):
             'sample': '%d full bs=%d KRN train steps of the oracle port (torch CPU, %d threads), %.2f s/step' % (steps_n, BATCH, cores, dt)}
 
 
+
+# ------------------------------------------------------------------------------------------------
+def _time_steps(fn, warm, k):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(k):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / k
+
+
+def secondary_workloads(dev, stepper, d_img, d_tgt, k=8):
+    """The other BASELINE.json configs on ONE GPU, device-resident inputs, CUDA events (ms per step, images/s):
+    configs[2] KRN + style augmentation every step, configs[3] DANN step (48 source + 48 target), configs[4] SPN bs=32."""
+    import torch
+    from oracle import ghiasi as ogh, synth                       # weights only (synthetic Ghiasi checkpoint)
+    from speedplusbaseline_b200.styleaug.styleAugmentor import StyleAugmentor
+    from speedplusbaseline_b200.nets.revgrad import RevGrad
+    from speedplusbaseline_b200.nets.spn import SpacecraftPoseNet
+    from speedplusbaseline_b200.optim import FusedAdamW
+    from speedplusbaseline_b200.core.dann import DANNTrainStep
+    from speedplusbaseline_b200.core.trainer import SPNTrainStep
+    out = {}
+    g = torch.Generator().manual_seed(1)
+    cov = torch.randn(100, 100, generator=g)
+    state = dict(ghiasi=synth.synth_state_dict(ogh.ghiasi_shapes(), 7), mean=torch.randn(1, 100, generator=g),
+                 cov=(cov @ cov.t() / 100).numpy(), base=torch.randn(100, generator=g))
+    aug = StyleAugmentor(0.5, dev, state=state)
+    ms = _time_steps(lambda: aug(d_img), 2, k)
+    out['styleaug_forward_bs48'] = {'ms': ms, 'images_per_sec': BATCH / ms * 1e3, 'tflops_reference_flops': 15.434 * BATCH / ms}
+    ms = _time_steps(lambda: stepper.step(aug(d_img), d_tgt), 2, k)
+    out['krn_train_with_styleaug_ratio1_bs48'] = {'ms': ms, 'images_per_sec': BATCH / ms * 1e3}
+    del aug
+    m = RevGrad(11, device=dev, seed=2021)
+    m.train()
+    opt = FusedAdamW(m._store, m.parameters(), lr=1e-3, weight_decay=0.01, clip_mode=1)
+    ds = DANNTrainStep(m, opt)
+    tgt_img = torch.rand_like(d_img)
+    ms = _time_steps(lambda: ds.step(d_img, d_tgt, tgt_img, 0.5), 3, k)
+    out['dann_step_48src_48tgt'] = {'ms': ms, 'images_per_sec': 2 * BATCH / ms * 1e3, 'source_images_per_sec': BATCH / ms * 1e3}
+    del m, opt, ds
+    torch.cuda.empty_cache()
+    spn = SpacecraftPoseNet.__new__(SpacecraftPoseNet)
+    torch.nn.Module.__init__(spn)
+    from speedplusbaseline_b200.spn_engine import SPNEngine
+    spn.engine = SPNEngine(5000, device=dev)
+    spn._register_store(spn.engine.store, spn.engine.key_order)
+    spn.engine.store.params.normal_(0.0, 0.01)                     # random init on the device (152 M parameters)
+    spn.train()
+    opt = FusedAdamW(spn._store, spn.parameters(), lr=1e-3, weight_decay=0.01, clip_mode=2)
+    ss = SPNTrainStep(spn, opt, use_graph=False)
+    x = torch.rand(32, 3, 227, 227, device=dev)
+    yc = torch.zeros(32, 5000, device=dev)
+    yc[:, :5] = 0.2
+    ms = _time_steps(lambda: ss.step(x, yc, yc), 2, k)
+    out['spn_train_bs32_dropout0.5'] = {'ms': ms, 'images_per_sec': 32 / ms * 1e3}
+    return out
+
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -132,6 +195,7 @@ def main():
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-out', default='')
+    ap.add_argument('--no-secondary', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -150,7 +214,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+        import datetime
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=90))
     W = max(3, args.warmup)
     K = max(1, args.steps)
 
@@ -214,11 +279,12 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
 
+    # per-launch CUDA-event profile of eager steps: every rank runs it (the steps contain the gradient allreduce)
+    prof = profiler.profile_krn_step(stepper, d_img, d_tgt, reps=3)
     if rank == 0:
         hbm, tf, which = _peaks()
         value = world * BATCH * K / (ms / 1e3)
         e2e = world * BATCH * K / (ms_e2e / 1e3)
-        prof = profiler.profile_krn_step(stepper, d_img, d_tgt, reps=3)
         dom = prof['dominant']
         roof = {'bound': 'hbm', 'kernel': dom['name'], 'achieved': dom['gbs'], 'peak': hbm, 'unit': 'GB/s',
                 'frac': dom['gbs'] / hbm, 'traffic': None, 'peak_source': which + ' (sustained copy)',
@@ -242,6 +308,11 @@ def main():
             'gpu_launches': launches_per_step * K, 'launches_per_step': launches_per_step,
             'clocks': clocks, 'roofline': roof, 'final_loss': final_loss,
         }
+        if not args.no_secondary and world == 1:
+            try:
+                line['secondary'] = secondary_workloads(dev, stepper, d_img, d_tgt)
+            except Exception as e:          # secondary numbers never invalidate the headline line
+                line['secondary'] = {'error': repr(e)[:300]}
         if not args.no_cpu_baseline and world == 1:
             line['cpu_baseline'] = cpu_baseline()
         print(json.dumps(line))
