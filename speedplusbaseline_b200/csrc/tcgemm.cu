@@ -53,6 +53,8 @@ struct TcgArgs {
     uint32_t op_stage_bytes, raw_stage_bytes;
     uint32_t off_raw, off_stg, off_stat, off_bar;   // dynamic smem carve-up (from the 1024-aligned base)
     uint32_t tmem_cols;
+    int nacc;                        // TMEM accumulator ring depth (2 or 4)
+    int split_epi;                   // one column chunk per tile: the two epilogue warp sets take alternate tiles
     void* out;
     const float* bias;
     int out_act, has_bnf;
@@ -338,10 +340,10 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.off_bar);
     uint64_t* full = bars;                    // [MAX_OP]  producers -> MMA
     uint64_t* empty = bars + MAX_OP;          // [MAX_OP]  MMA -> producers
-    uint64_t* tfull = bars + 2 * MAX_OP;      // [2]       MMA -> epilogue
-    uint64_t* tempty = bars + 2 * MAX_OP + 2; // [2]       epilogue -> MMA
-    uint64_t* bfull = bars + 2 * MAX_OP + 4;  // [1]       producers -> MMA: resident B converted
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_OP + 5);
+    uint64_t* tfull = bars + 2 * MAX_OP;      // [4]       MMA -> epilogue
+    uint64_t* tempty = bars + 2 * MAX_OP + 4; // [4]       epilogue -> MMA
+    uint64_t* bfull = bars + 2 * MAX_OP + 8;  // [1]       producers -> MMA: resident B converted
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_OP + 9);
     int* s_flag = reinterpret_cast<int*>(tmem_slot + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -349,7 +351,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
 
     if (tid == 0) {
         for (int i = 0; i < MAX_OP; ++i) { tc::mbar_init(&full[i], PROD_T / 32); tc::mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], EPI_W); }
+        for (int i = 0; i < 4; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], g.split_epi ? EPI_W / EPI_SETS : EPI_W); }
         tc::mbar_init(bfull, PROD_T / 32);
         tc::mbar_fence_init();
     }
@@ -469,12 +471,11 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
                                       : tc::smem_desc(base + ks * KSTEP_MM, LBO_MM, SBO_MM, LT_MM);
         };
         if (g.b_res) { mbar_wait_guard(bfull, 0, g.wait_mode); tc::tc_fence_after(); }
-        int ni = 0, os = 0;
-        uint32_t fpar = 0;
-        for (int it = blockIdx.x; it < total; it += gridDim.x, ++ni) {
+        int os = 0, acc = 0;
+        uint32_t fpar = 0, tpar = 1;
+        for (int it = blockIdx.x; it < total; it += gridDim.x) {
             const Item w = get_item(g, it);
-            const int acc = ni & 1;
-            mbar_wait_guard(&tempty[acc], ((ni >> 1) & 1) ^ 1, g.wait_mode);
+            mbar_wait_guard(&tempty[acc], tpar, g.wait_mode);
             tc::tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * g.BN;
             for (int kb = w.kb0; kb < w.kb1; ++kb) {
@@ -502,6 +503,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
                 __syncwarp();
                 if (++os == g.n_op) { os = 0; fpar ^= 1; }
             }
+            if (++acc == g.nacc) { acc = 0; tpar ^= 1; }
         }
     } else {
         // ======================================= EPILOGUE ========================================
@@ -518,7 +520,8 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
         float* outF = reinterpret_cast<float*>(g.out);
         const int nchunks = (g.BN + 31) >> 5;
         int last_chunk = -1;                            // last chunk this warp reads from TMEM
-        for (int c = half; c < nchunks; c += EPI_SETS) last_chunk = c;
+        const int c_first = g.split_epi ? 0 : half, c_step = g.split_epi ? 1 : EPI_SETS;
+        for (int c = c_first; c < nchunks; c += c_step) last_chunk = c;
         int ni = 0;
         int cur_q0 = -1;
         auto flush = [&](int q0) {
@@ -539,12 +542,16 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
             }
             epi_bar();
         };
+        int acc = -1;
+        uint32_t tpar = 1;
         for (int it = blockIdx.x; it < total; it += gridDim.x, ++ni) {
+            if (++acc == g.nacc) acc = 0;
+            if (acc == 0) tpar ^= 1;
+            if (g.split_epi && (ni & 1) != half) continue;      // the other warp set drains this tile
             const Item w = get_item(g, it);
-            const int acc = ni & 1;
             if (do_stats && cur_q0 >= 0 && cur_q0 != w.q0) flush(cur_q0);
             cur_q0 = w.q0;
-            mbar_wait_sleep(&tfull[acc], (ni >> 1) & 1);
+            mbar_wait_sleep(&tfull[acc], tpar);
             tc::tc_fence_after();
             const uint32_t t_row = tmem_base + acc * g.BN + ((uint32_t)(lq * 32) << 16);
             if (last_chunk < 0) {                        // nothing to read for this warp: release immediately
@@ -552,7 +559,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&tempty[acc]);
             }
-            for (int ci = half; ci < nchunks; ci += EPI_SETS) {
+            for (int ci = c_first; ci < nchunks; ci += c_step) {
                 const int c0 = ci * 32;
                 const int ncol = min(32, g.BN - c0);
                 uint32_t r[32];
@@ -662,7 +669,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
             }
         }
         if (do_stats) {
-            if (cur_q0 >= 0) flush(cur_q0);
+            flush(cur_q0 >= 0 ? cur_q0 : 0);       // every epilogue warp takes part (bar.sync), even one that drained no tile
             // elect the last CTA of the grid: it turns the accumulated sums into scale/shift (fwd) or dy coefficients (bwd)
             __threadfence();
             epi_bar();
@@ -765,8 +772,10 @@ int launch_cfg(TcgArgs& a, cudaStream_t st) {
     a.kb_per_split = ceil_div(a.nkb, a.splits);
     a.splits = ceil_div(a.nkb, a.kb_per_split);
     const uint32_t smem = a.off_bar + 256 + 1024;
+    a.nacc = 4 * BN <= 512 ? 4 : 2;
+    a.split_epi = (BN <= 32 && numQt == 1 && EPI_SETS == 2) ? 1 : 0;
     uint32_t cols = 32;
-    while (cols < (uint32_t)(2 * BN)) cols <<= 1;
+    while (cols < (uint32_t)(a.nacc * BN)) cols <<= 1;
     a.tmem_cols = cols;
     const int total = numPt * numQt * a.splits;
     const int grid = total < NUM_SMS ? total : NUM_SMS;
