@@ -286,8 +286,15 @@ def main():
         value = world * BATCH * K / (ms / 1e3)
         e2e = world * BATCH * K / (ms_e2e / 1e3)
         dom = prof['dominant']
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get(dom['name'])
+            if tj:
+                traffic = tj['dram_read'] + tj['dram_write']
+        except Exception:
+            pass
         roof = {'bound': 'hbm', 'kernel': dom['name'], 'achieved': dom['gbs'], 'peak': hbm, 'unit': 'GB/s',
-                'frac': dom['gbs'] / hbm, 'traffic': None, 'peak_source': which + ' (sustained copy)',
+                'frac': dom['gbs'] / hbm, 'traffic': traffic, 'peak_source': which + ' (sustained copy)',
                 'share_of_step': dom['share'], 'us_per_launch': dom['us'], 'algorithmic_bytes_per_launch': dom['bytes'],
                 'step_roofline_frac': prof['step_roofline_ms'] / (ms / K),
                 'step_algorithmic_gb': prof['step_bytes'] / 1e9}
