@@ -40,6 +40,13 @@ class SyntheticLoader:
         H, W = cfg.input_shape[0], cfg.input_shape[1]
         self.images = torch.rand(cfg.batch_size, 3, H, W, generator=g)
         self.target = torch.rand(cfg.batch_size, 2, cfg.num_keypoints, generator=g)
+        self.spn = cfg.model_name == 'spn' and not cfg.dann
+        if self.spn:        # SPNDataset.py:83-94: soft n-hot attitude-class / weight targets
+            t = torch.zeros(cfg.batch_size, cfg.num_classes)
+            for b in range(cfg.batch_size):
+                idx = torch.randperm(cfg.num_classes, generator=g)[:cfg.num_neighbors]
+                t[b, idx] = 1.0 / cfg.num_neighbors
+            self.yc, self.yw = t, t.clone()
         if pin and torch.cuda.is_available():
             self.images, self.target = self.images.pin_memory(), self.target.pin_memory()
 
@@ -48,7 +55,10 @@ class SyntheticLoader:
 
     def __iter__(self):
         for _ in range(self.n):
-            yield (self.images, self.target) if self.labels else self.images
+            if self.spn:
+                yield (self.images, self.yc, self.yw)
+            else:
+                yield (self.images, self.target) if self.labels else self.images
 
 
 def make_loaders(cfg, specs):

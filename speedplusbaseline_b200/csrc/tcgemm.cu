@@ -462,14 +462,14 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
         constexpr uint32_t KSTEP_KM = 32, KSTEP_MM = (E::TF32 ? 8 : 16) * 128;
         constexpr uint32_t LBO_MM = E::KE * 128, SBO_MM = E::TF32 ? 512 : 1024;
         constexpr uint32_t LT_MM = E::TF32 ? tc::SWZ_128B_BASE32B : tc::SWZ_128B;
-        auto adesc = [&](uint32_t base, int ks) {
-            return ALAY == TCG_LAY_KM ? tc::smem_desc(base + ks * KSTEP_KM, 0, 1024, tc::SWZ_128B)
-                                      : tc::smem_desc(base + ks * KSTEP_MM, LBO_MM, SBO_MM, LT_MM);
-        };
-        auto bdesc = [&](uint32_t base, int ks) {
-            return BLAY == TCG_LAY_KM ? tc::smem_desc(base + ks * KSTEP_KM, 0, 1024, tc::SWZ_128B)
-                                      : tc::smem_desc(base + ks * KSTEP_MM, LBO_MM, SBO_MM, LT_MM);
-        };
+        // shared-memory descriptors: the high word is a per-operand constant, the low word is (address >> 4) plus the
+        // leading-byte-offset field -- per k-step the issuing thread only adds a constant (it is the serial bottleneck
+        // of short tiles, so every instruction here counts)
+        constexpr uint32_t A_STEP = (ALAY == TCG_LAY_KM ? KSTEP_KM : KSTEP_MM) >> 4, B_STEP = (BLAY == TCG_LAY_KM ? KSTEP_KM : KSTEP_MM) >> 4;
+        constexpr uint32_t A_LBO = ALAY == TCG_LAY_KM ? 0u : ((LBO_MM >> 4) << 16), B_LBO = BLAY == TCG_LAY_KM ? 0u : ((LBO_MM >> 4) << 16);
+        constexpr uint32_t A_HIW = ((ALAY == TCG_LAY_KM ? 1024u : SBO_MM) >> 4) | (1u << 14) | ((uint32_t)(ALAY == TCG_LAY_KM ? tc::SWZ_128B : LT_MM) << 29);
+        constexpr uint32_t B_HIW = ((BLAY == TCG_LAY_KM ? 1024u : SBO_MM) >> 4) | (1u << 14) | ((uint32_t)(BLAY == TCG_LAY_KM ? tc::SWZ_128B : LT_MM) << 29);
+        auto mk = [](uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); };
         if (g.b_res) { mbar_wait_guard(bfull, 0, g.wait_mode); tc::tc_fence_after(); }
         int os = 0, acc = 0;
         uint32_t fpar = 0, tpar = 1;
@@ -487,14 +487,19 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
                     const uint32_t b_lo = b_hi + g.b_op_bytes;
                     // a K-major operand only holds the active chunks of a partial last k-block: never read beyond them
                     const int nks = ((ALAY == TCG_LAY_KM || BLAY == TCG_LAY_KM) && kb == g.nkb - 1) ? g.nks_last : 4;
-                    for (int ks = 0; ks < nks; ++ks) {
-                        const uint32_t accum = (kb > w.kb0 || ks > 0) ? 1u : 0u;
-                        if (E::TF32) {
-                            tc::umma<true>(d_tmem, adesc(a_lo, ks), bdesc(b_hi, ks), idesc, accum);
-                            tc::umma<true>(d_tmem, adesc(a_hi, ks), bdesc(b_lo, ks), idesc, 1u);
-                            tc::umma<true>(d_tmem, adesc(a_hi, ks), bdesc(b_hi, ks), idesc, 1u);
-                        } else {
-                            tc::umma<false>(d_tmem, adesc(a_hi, ks), bdesc(b_hi, ks), idesc, accum);
+                    const uint32_t al = (a_lo >> 4) + A_LBO, ah = (a_hi >> 4) + A_LBO, bl = (b_lo >> 4) + B_LBO, bh = (b_hi >> 4) + B_LBO;
+                    const uint32_t first = kb > w.kb0 ? 1u : 0u;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        if (ks < nks) {
+                            const uint32_t accum = ks > 0 ? 1u : first;
+                            if (E::TF32) {
+                                tc::umma<true>(d_tmem, mk(al + ks * A_STEP, A_HIW), mk(bh + ks * B_STEP, B_HIW), idesc, accum);
+                                tc::umma<true>(d_tmem, mk(ah + ks * A_STEP, A_HIW), mk(bl + ks * B_STEP, B_HIW), idesc, 1u);
+                                tc::umma<true>(d_tmem, mk(ah + ks * A_STEP, A_HIW), mk(bh + ks * B_STEP, B_HIW), idesc, 1u);
+                            } else {
+                                tc::umma<false>(d_tmem, mk(ah + ks * A_STEP, A_HIW), mk(bh + ks * B_STEP, B_HIW), idesc, accum);
+                            }
                         }
                     }
                     tc::umma_commit(&empty[os]);
