@@ -241,11 +241,11 @@ int b200sp_im2col(const float *x, float *col, int B, int H, int W, int C, int c_
 int b200sp_col2im(const float *dcol, float *dx, const float *act_mask, int B, int H, int W, int C, int c_off, int Cg, int k,
                   int stride, int pad, int Kp, void *stream);
 /* MaxPool2d(3,2) [+ LocalResponseNorm(size 2, alpha, beta, k=1)] (spn.py:61-62,66-67,77); pooled (may be NULL) keeps the
- * pre-LRN values for the backward */
-int b200sp_pool_lrn_fwd(const float *x, float *pooled, float *out, int B, int H, int W, int C, int lrn, float alpha, float beta,
-                        void *stream);
-int b200sp_pool_lrn_bwd(const float *g_out, const float *pooled, const float *x, float *scratch, float *dx, int B, int H, int W,
-                        int C, int lrn, float alpha, float beta, int relu_mask, void *stream);
+ * pre-LRN values and amax (may be NULL in eval) the first-maximum index 0..8 of every window for the backward */
+int b200sp_pool_lrn_fwd(const float *x, float *pooled, float *out, uint8_t *amax, int B, int H, int W, int C, int lrn, float alpha,
+                        float beta, void *stream);
+int b200sp_pool_lrn_bwd(const float *g_out, const float *pooled, const float *x, const uint8_t *amax, float *scratch, float *dx,
+                        int B, int H, int W, int C, int lrn, float alpha, float beta, int relu_mask, void *stream);
 /* Dropout(p) (spn.py:81,85,92,96): counter-based mask from `seed` (not torch's RNG stream); mask saved for backward */
 int b200sp_dropout_fwd(const float *x, float *out, uint8_t *mask, int64_t n, float p, uint64_t seed, void *stream);
 int b200sp_dropout_bwd(float *g, const uint8_t *mask, int64_t n, float p, void *stream);

@@ -107,8 +107,8 @@ _SIGS = {
     'b200sp_colsum_f32': ([PVT, vp, i32, i32, i32, vp], i32),
     'b200sp_im2col': ([vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp], i32),
     'b200sp_col2im': ([vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp], i32),
-    'b200sp_pool_lrn_fwd': ([vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp], i32),
-    'b200sp_pool_lrn_bwd': ([vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, i32, vp], i32),
+    'b200sp_pool_lrn_fwd': ([vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp], i32),
+    'b200sp_pool_lrn_bwd': ([vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, i32, vp], i32),
     'b200sp_dropout_fwd': ([vp, vp, vp, i64, f32, C.c_uint64, vp], i32),
     'b200sp_dropout_bwd': ([vp, vp, i64, f32, vp], i32),
     'b200sp_soft_ce': ([vp, vp, vp, vp, i32, i32, f32, vp], i32),

@@ -307,10 +307,26 @@ inline b200sp_vtensor plain_vt(const void* p) {
 
 // B200SP_GEMM=legacy forces the mma.sync kernels (A/B testing); default is the tcgen05 path with
 // the mma.sync kernel as the fallback for shapes it does not cover (odd widths, unaligned pointers).
-inline bool use_tc() {
+inline int gemm_mode() {      // 0 legacy only, 1 measured dispatch (default), 2 tcgen05 only
     static int v = -1;
-    if (v < 0) { const char* e = getenv("B200SP_GEMM"); v = (e && e[0] == 'l') ? 0 : 1; }
-    return v == 1;
+    if (v < 0) { const char* e = getenv("B200SP_GEMM"); v = !e ? 1 : (e[0] == 'l' ? 0 : (e[0] == 't' ? 2 : 1)); }
+    return v;
+}
+// Measured on B200 (profiles/r1_e_gemm_dispatch.txt): for long-M layers with a small N x K the register-tiled
+// CUDA-core kernel (exact fp32 FFMA, streaming split-M) beats the tcgen05 pipeline, whose 128-row tiles are mostly
+// padding there and whose per-k-block hand-offs dominate.  op: 0 fwd, 1 dgrad, 2 wgrad.
+inline bool prefer_cuda_cores(int op, int M, int N, int K) {
+    if (M < 9408) return false;
+    if (op == 2) return (long long)N * K <= 24576;
+    static const int fwd_nk[][2] = {{16, 32}, {32, 144}, {32, 192}};
+    static const int dgrad_nk[][2] = {{24, 144}, {32, 144}, {192, 32}, {64, 192}};
+    if (op == 0) { for (auto& e : fwd_nk) if (e[0] == N && e[1] == K) return true; }
+    if (op == 1) { for (auto& e : dgrad_nk) if (e[0] == N && e[1] == K) return true; }
+    return false;
+}
+inline bool use_tc(int op, int M, int N, int K) {
+    const int m = gemm_mode();
+    return m == 2 || (m == 1 && !prefer_cuda_cores(op, M, N, K));
 }
 
 }  // namespace
@@ -318,7 +334,7 @@ inline bool use_tc() {
 extern "C" int b200sp_pw_fwd(const b200sp_vtensor* x, const float* w, const float* bias, int out_act, void* y,
                              const b200sp_bnfwd* bn, int M, int N, int K, int dtype, void* stream) {
     if (!x || x->mode == B200SP_VT_DY) return B200SP_EINVAL;
-    if (use_tc() && dtype == B200SP_F32) {
+    if (use_tc(0, M, N, K) && dtype == B200SP_F32) {
         TcgProblem p = {};
         p.a = *x; p.b = plain_vt(w); p.a_lay = TCG_LAY_KM; p.b_lay = TCG_LAY_KM;
         p.P = M; p.Q = N; p.R = K; p.lda = K; p.ldb = K; p.epi = TCG_EPI_FWD; p.dtype = dtype;
@@ -341,7 +357,7 @@ extern "C" int b200sp_pw_fwd(const b200sp_vtensor* x, const float* w, const floa
 extern "C" int b200sp_pw_dgrad(const b200sp_vtensor* dy, const float* w, const void* skip, float scale_out, void* g,
                                const b200sp_bnbwd* bn, int M, int N, int K, int dtype, void* stream) {
     if (!dy) return B200SP_EINVAL;
-    if (use_tc() && dtype == B200SP_F32) {
+    if (use_tc(1, M, N, K) && dtype == B200SP_F32) {
         TcgProblem p = {};
         p.a = *dy; p.b = plain_vt(w); p.a_lay = TCG_LAY_KM; p.b_lay = TCG_LAY_MM;
         p.P = M; p.Q = K; p.R = N; p.lda = N; p.ldb = K; p.epi = TCG_EPI_DGRAD; p.dtype = dtype;
@@ -368,7 +384,7 @@ extern "C" int b200sp_pw_dgrad(const b200sp_vtensor* dy, const float* w, const v
 extern "C" int b200sp_pw_wgrad(const b200sp_vtensor* dy, const b200sp_vtensor* x, float* dw, float* dbias,
                                int M, int N, int K, int dtype, void* stream) {
     if (!dy || !x || x->mode == B200SP_VT_DY) return B200SP_EINVAL;
-    if (use_tc() && dtype == B200SP_F32) {
+    if (use_tc(2, M, N, K) && dtype == B200SP_F32) {
         TcgProblem p = {};
         p.a = *dy; p.b = *x; p.a_lay = TCG_LAY_MM; p.b_lay = TCG_LAY_MM;
         p.P = N; p.Q = K; p.R = M; p.lda = N; p.ldb = K; p.epi = TCG_EPI_ATOMIC; p.dtype = dtype;

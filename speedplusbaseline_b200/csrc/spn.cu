@@ -15,23 +15,42 @@ inline int sp_grid(long long n) {
     return (int)(g < 1 ? 1 : (g < cap ? g : cap));
 }
 
-// col[m][(kh*k + kw)*Cg + c] = x[b, oh*s - p + kh, ow*s - p + kw, c_off + c]  (0 outside);  K padded to Kp with zeros
+// col[m][(kh*k + kw)*Cg + c] = x[b, oh*s - p + kh, ow*s - p + kw, c_off + c]  (0 outside);  K padded to Kp with zeros.
+// One thread = one 16-byte store (4 consecutive columns); when Cg % 4 == 0 (every layer but conv1) the 4 columns are
+// 4 consecutive channels of one tap, i.e. one 16-byte NHWC load.
 __global__ void __launch_bounds__(SP_NT) im2col_kernel(const float* __restrict__ x, float* __restrict__ col, int B, int H, int W, int C,
                                                       int c_off, int Cg, int k, int s, int p, int Ho, int Wo, int Kp, int nchw) {
-    const long long n = (long long)B * Ho * Wo * Kp;
+    const int K4 = Kp >> 2, Kreal = k * k * Cg;
+    const long long n = (long long)B * Ho * Wo * K4;
+    const bool vec = !nchw && (Cg & 3) == 0 && (C & 3) == 0 && (c_off & 3) == 0;
     for (long long i = (long long)blockIdx.x * SP_NT + threadIdx.x; i < n; i += (long long)gridDim.x * SP_NT) {
-        const int kk = (int)(i % Kp);
-        const long long m = i / Kp;
-        float v = 0.f;
-        if (kk < k * k * Cg) {
-            const int c = kk % Cg, t = kk / Cg, kw = t % k, kh = t / k;
-            const int ow = (int)(m % Wo), oh = (int)((m / Wo) % Ho), b = (int)(m / ((long long)Wo * Ho));
-            const int ih = oh * s - p + kh, iw = ow * s - p + kw;
-            if (ih >= 0 && ih < H && iw >= 0 && iw < W)
-                v = nchw ? __ldg(x + (((size_t)b * C + c_off + c) * H + ih) * W + iw)
-                         : __ldg(x + (((size_t)b * H + ih) * W + iw) * C + c_off + c);
+        const int kk = (int)(i % K4) * 4;
+        const long long m = i / K4;
+        const int ow = (int)(m % Wo), oh = (int)((m / Wo) % Ho), b = (int)(m / ((long long)Wo * Ho));
+        float4 v = f4zero();
+        if (vec) {
+            if (kk < Kreal) {
+                const int c = kk % Cg, t = kk / Cg, kw = t % k, kh = t / k;
+                const int ih = oh * s - p + kh, iw = ow * s - p + kw;
+                if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = ldg4(x + (((size_t)b * H + ih) * W + iw) * C + c_off + c);
+            }
+        } else {
+            float e[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int q = kk + j;
+                e[j] = 0.f;
+                if (q < Kreal) {
+                    const int c = q % Cg, t = q / Cg, kw = t % k, kh = t / k;
+                    const int ih = oh * s - p + kh, iw = ow * s - p + kw;
+                    if (ih >= 0 && ih < H && iw >= 0 && iw < W)
+                        e[j] = nchw ? __ldg(x + (((size_t)b * C + c_off + c) * H + ih) * W + iw)
+                                    : __ldg(x + (((size_t)b * H + ih) * W + iw) * C + c_off + c);
+                }
+            }
+            v = make_float4(e[0], e[1], e[2], e[3]);
         }
-        col[i] = v;
+        *reinterpret_cast<float4*>(col + i * 4) = v;
     }
 }
 
@@ -69,7 +88,8 @@ __global__ void __launch_bounds__(SP_NT) col2im_kernel(const float* __restrict__
 
 // MaxPool2d(3, 2) then optional LocalResponseNorm(size 2): out = p / (1 + alpha/2 (p[c-1]^2 + p[c]^2))^beta
 __global__ void __launch_bounds__(SP_NT) pool_lrn_fwd_kernel(const float* __restrict__ x, float* __restrict__ pooled, float* __restrict__ out,
-                                                            int B, int H, int W, int C, int Ho, int Wo, int lrn, float alpha, float beta) {
+                                                            uint8_t* __restrict__ amax, int B, int H, int W, int C, int Ho, int Wo, int lrn,
+                                                            float alpha, float beta) {
     const long long n = (long long)B * Ho * Wo * C;
     for (long long i = (long long)blockIdx.x * SP_NT + threadIdx.x; i < n; i += (long long)gridDim.x * SP_NT) {
         const int c = (int)(i % C);
@@ -77,15 +97,19 @@ __global__ void __launch_bounds__(SP_NT) pool_lrn_fwd_kernel(const float* __rest
         const int ow = (int)(r % Wo); r /= Wo;
         const int oh = (int)(r % Ho);
         const int b = (int)(r / Ho);
+        int am = 0;
         auto pool = [&](int cc) {
             float m = -3.4e38f;
             for (int kh = 0; kh < 3; ++kh)
-                for (int kw = 0; kw < 3; ++kw)
-                    m = fmaxf(m, __ldg(x + (((size_t)b * H + oh * 2 + kh) * W + ow * 2 + kw) * C + cc));
+                for (int kw = 0; kw < 3; ++kw) {
+                    const float v = __ldg(x + (((size_t)b * H + oh * 2 + kh) * W + ow * 2 + kw) * C + cc);
+                    if (v > m) { m = v; if (cc == c) am = kh * 3 + kw; }      // first maximum wins (torch max_pool2d)
+                }
             return m;
         };
         const float pc = pool(c);
         if (pooled) pooled[i] = pc;
+        if (amax) amax[i] = (uint8_t)am;
         if (lrn) {
             const float pm = c > 0 ? pool(c - 1) : 0.f;
             const float d = 1.f + 0.5f * alpha * (pm * pm + pc * pc);
@@ -117,9 +141,9 @@ __global__ void __launch_bounds__(SP_NT) lrn_bwd_kernel(const float* __restrict_
 }
 
 // MaxPool2d(3,2) backward in gather form: dx = relu'(x) * sum over the (<= 4) windows that contain this element and
-// whose FIRST maximum (row-major scan, the index torch's max_pool2d records) is this element.
-__global__ void __launch_bounds__(SP_NT) pool_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ x, float* __restrict__ dx,
-                                                        int B, int H, int W, int C, int Ho, int Wo, int relu_mask) {
+// whose recorded first-maximum index (amax, written by the forward) is this element.
+__global__ void __launch_bounds__(SP_NT) pool_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ x, const uint8_t* __restrict__ amax,
+                                                        float* __restrict__ dx, int B, int H, int W, int C, int Ho, int Wo, int relu_mask) {
     const long long n = (long long)B * H * W * C;
     for (long long i = (long long)blockIdx.x * SP_NT + threadIdx.x; i < n; i += (long long)gridDim.x * SP_NT) {
         const int c = (int)(i % C);
@@ -127,23 +151,16 @@ __global__ void __launch_bounds__(SP_NT) pool_bwd_kernel(const float* __restrict
         const int iw = (int)(r % W); r /= W;
         const int ih = (int)(r % H);
         const int b = (int)(r / H);
-        const float xv = x[i];
         float acc = 0.f;
-        if (!(relu_mask && !(xv > 0.f))) {
+        if (!(relu_mask && !(x[i] > 0.f))) {
             for (int oh = max(0, (ih - 1) / 2); oh <= min(Ho - 1, ih / 2); ++oh) {
-                if (oh * 2 > ih || oh * 2 + 2 < ih) continue;
+                const int kh = ih - oh * 2;
+                if (kh < 0 || kh > 2) continue;
                 for (int ow = max(0, (iw - 1) / 2); ow <= min(Wo - 1, iw / 2); ++ow) {
-                    if (ow * 2 > iw || ow * 2 + 2 < iw) continue;
-                    // is (ih, iw) the first maximum of window (oh, ow)?
-                    bool first = true;
-                    for (int kh = 0; kh < 3 && first; ++kh)
-                        for (int kw = 0; kw < 3; ++kw) {
-                            const int yh = oh * 2 + kh, yw = ow * 2 + kw;
-                            const float v = __ldg(x + (((size_t)b * H + yh) * W + yw) * C + c);
-                            const bool before = yh < ih || (yh == ih && yw < iw);
-                            if (before ? v >= xv : v > xv) { first = false; break; }
-                        }
-                    if (first) acc += __ldg(dp + (((size_t)b * Ho + oh) * Wo + ow) * C + c);
+                    const int kw = iw - ow * 2;
+                    if (kw < 0 || kw > 2) continue;
+                    const size_t o = (((size_t)b * Ho + oh) * Wo + ow) * C + c;
+                    if (amax[o] == kh * 3 + kw) acc += __ldg(dp + o);
                 }
             }
         }
@@ -221,8 +238,8 @@ __global__ void __launch_bounds__(SP_NT) relu_mask_kernel(float* __restrict__ g,
 extern "C" int b200sp_im2col(const float* x, float* col, int B, int H, int W, int C, int c_off, int Cg, int k, int stride, int pad,
                              int Kp, int nchw, void* stream) {
     const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
-    if (Kp < k * k * Cg || Ho < 1 || Wo < 1) return B200SP_EINVAL;
-    im2col_kernel<<<sp_grid((long long)B * Ho * Wo * Kp), SP_NT, 0, (cudaStream_t)stream>>>(x, col, B, H, W, C, c_off, Cg, k, stride, pad, Ho, Wo, Kp, nchw);
+    if (Kp < k * k * Cg || (Kp & 3) || Ho < 1 || Wo < 1) return B200SP_EINVAL;
+    im2col_kernel<<<sp_grid((long long)B * Ho * Wo * (Kp / 4)), SP_NT, 0, (cudaStream_t)stream>>>(x, col, B, H, W, C, c_off, Cg, k, stride, pad, Ho, Wo, Kp, nchw);
     B200SP_COUNT_LAUNCH();
     B200SP_RETURN_LAST();
 }
@@ -235,16 +252,17 @@ extern "C" int b200sp_col2im(const float* dcol, float* dx, const float* act_mask
     B200SP_RETURN_LAST();
 }
 
-extern "C" int b200sp_pool_lrn_fwd(const float* x, float* pooled, float* out, int B, int H, int W, int C, int lrn, float alpha, float beta,
-                                   void* stream) {
+extern "C" int b200sp_pool_lrn_fwd(const float* x, float* pooled, float* out, uint8_t* amax, int B, int H, int W, int C, int lrn, float alpha,
+                                   float beta, void* stream) {
     const int Ho = (H - 3) / 2 + 1, Wo = (W - 3) / 2 + 1;
-    pool_lrn_fwd_kernel<<<sp_grid((long long)B * Ho * Wo * C), SP_NT, 0, (cudaStream_t)stream>>>(x, pooled, out, B, H, W, C, Ho, Wo, lrn, alpha, beta);
+    pool_lrn_fwd_kernel<<<sp_grid((long long)B * Ho * Wo * C), SP_NT, 0, (cudaStream_t)stream>>>(x, pooled, out, amax, B, H, W, C, Ho, Wo, lrn, alpha, beta);
     B200SP_COUNT_LAUNCH();
     B200SP_RETURN_LAST();
 }
 
-extern "C" int b200sp_pool_lrn_bwd(const float* g_out, const float* pooled, const float* x, float* scratch, float* dx, int B, int H, int W,
-                                   int C, int lrn, float alpha, float beta, int relu_mask, void* stream) {
+extern "C" int b200sp_pool_lrn_bwd(const float* g_out, const float* pooled, const float* x, const uint8_t* amax, float* scratch, float* dx,
+                                   int B, int H, int W, int C, int lrn, float alpha, float beta, int relu_mask, void* stream) {
+    if (!amax) return B200SP_EINVAL;
     const int Ho = (H - 3) / 2 + 1, Wo = (W - 3) / 2 + 1;
     const float* dp = g_out;
     if (lrn) {
@@ -252,7 +270,7 @@ extern "C" int b200sp_pool_lrn_bwd(const float* g_out, const float* pooled, cons
         B200SP_COUNT_LAUNCH();
         dp = scratch;
     }
-    pool_bwd_kernel<<<sp_grid((long long)B * H * W * C), SP_NT, 0, (cudaStream_t)stream>>>(dp, x, dx, B, H, W, C, Ho, Wo, relu_mask);
+    pool_bwd_kernel<<<sp_grid((long long)B * H * W * C), SP_NT, 0, (cudaStream_t)stream>>>(dp, x, amax, dx, B, H, W, C, Ho, Wo, relu_mask);
     B200SP_COUNT_LAUNCH();
     B200SP_RETURN_LAST();
 }

@@ -136,18 +136,21 @@ class SPNEngine:
         a1, H1, W1 = self._conv_fwd(CONVS[0], images, B, H, W, nchw=True)
         Hp1, Wp1 = (H1 - 3) // 2 + 1, (W1 - 3) // 2 + 1
         p1, n1 = self._buf('p1', (B, Hp1, Wp1, 96)), self._buf('n1', (B, Hp1, Wp1, 96))
-        L.call('b200sp_pool_lrn_fwd', a1.data_ptr(), p1.data_ptr(), n1.data_ptr(), B, H1, W1, 96, 1, LRN_ALPHA, LRN_BETA, sp)
+        am1 = self._buf('am1', (B, Hp1, Wp1, 96), torch.uint8)
+        L.call('b200sp_pool_lrn_fwd', a1.data_ptr(), p1.data_ptr(), n1.data_ptr(), am1.data_ptr(), B, H1, W1, 96, 1, LRN_ALPHA, LRN_BETA, sp)
         a2, H2, W2 = self._conv_fwd(CONVS[1], n1, B, Hp1, Wp1)
         Hp2, Wp2 = (H2 - 3) // 2 + 1, (W2 - 3) // 2 + 1
         p2, n2 = self._buf('p2', (B, Hp2, Wp2, 256)), self._buf('n2', (B, Hp2, Wp2, 256))
-        L.call('b200sp_pool_lrn_fwd', a2.data_ptr(), p2.data_ptr(), n2.data_ptr(), B, H2, W2, 256, 1, LRN_ALPHA, LRN_BETA, sp)
+        am2 = self._buf('am2', (B, Hp2, Wp2, 256), torch.uint8)
+        L.call('b200sp_pool_lrn_fwd', a2.data_ptr(), p2.data_ptr(), n2.data_ptr(), am2.data_ptr(), B, H2, W2, 256, 1, LRN_ALPHA, LRN_BETA, sp)
         a3, H3, W3 = self._conv_fwd(CONVS[2], n2, B, Hp2, Wp2)
         a4, _, _ = self._conv_fwd(CONVS[3], a3, B, H3, W3)
         a5, _, _ = self._conv_fwd(CONVS[4], a4, B, H3, W3)
         Hp5, Wp5 = (H3 - 3) // 2 + 1, (W3 - 3) // 2 + 1
         assert Hp5 * Wp5 * 256 == 9216, 'SPN needs 227x227 inputs (spn.py:80: 6*6*256 features)'
         f = self._buf('f', (B, Hp5, Wp5, 256))
-        L.call('b200sp_pool_lrn_fwd', a5.data_ptr(), None, f.data_ptr(), B, H3, W3, 256, 0, 0.0, 0.0, sp)
+        am5 = self._buf('am5', (B, Hp5, Wp5, 256), torch.uint8)
+        L.call('b200sp_pool_lrn_fwd', a5.data_ptr(), None, f.data_ptr(), am5.data_ptr(), B, H3, W3, 256, 0, 0.0, 0.0, sp)
         self.geo = dict(H1=H1, W1=W1, Hp1=Hp1, Wp1=Wp1, H2=H2, W2=W2, Hp2=Hp2, Wp2=Wp2, H3=H3, W3=W3)
         self._dcol_elems = max(B * H2 * W2 * 1200, B * H3 * W3 * 2304)
         drop = train and self.drop_p > 0
@@ -203,7 +206,7 @@ class SPNEngine:
         H3, W3 = g['H3'], g['W3']
         scratch = self._buf('lrn_scratch', (max(bf['p1'].numel(), bf['p2'].numel()),))
         da5 = self._buf('da5', tuple(a5.shape))
-        L.call('b200sp_pool_lrn_bwd', df.data_ptr(), None, a5.data_ptr(), None, da5.data_ptr(), B, H3, W3, 256, 0, 0.0, 0.0, 1, sp)
+        L.call('b200sp_pool_lrn_bwd', df.data_ptr(), None, a5.data_ptr(), bf['am5'].data_ptr(), None, da5.data_ptr(), B, H3, W3, 256, 0, 0.0, 0.0, 1, sp)
         da4 = self._buf('da4', tuple(a4.shape))
         self._conv_bwd(CONVS[4], da5, (B, H3, W3), da4, a4)
         da3 = self._buf('da3', tuple(a3.shape))
@@ -211,11 +214,11 @@ class SPNEngine:
         dn2 = self._buf('dn2', tuple(bf['n2'].shape))
         self._conv_bwd(CONVS[2], da3, (B, g['Hp2'], g['Wp2']), dn2, None)
         da2 = self._buf('da2', tuple(a2.shape))
-        L.call('b200sp_pool_lrn_bwd', dn2.data_ptr(), bf['p2'].data_ptr(), a2.data_ptr(), scratch.data_ptr(), da2.data_ptr(),
+        L.call('b200sp_pool_lrn_bwd', dn2.data_ptr(), bf['p2'].data_ptr(), a2.data_ptr(), bf['am2'].data_ptr(), scratch.data_ptr(), da2.data_ptr(),
                B, g['H2'], g['W2'], 256, 1, LRN_ALPHA, LRN_BETA, 1, sp)
         dn1 = self._buf('dn1', tuple(bf['n1'].shape))
         self._conv_bwd(CONVS[1], da2, (B, g['Hp1'], g['Wp1']), dn1, None)
         da1 = self._buf('da1', tuple(a1.shape))
-        L.call('b200sp_pool_lrn_bwd', dn1.data_ptr(), bf['p1'].data_ptr(), a1.data_ptr(), scratch.data_ptr(), da1.data_ptr(),
+        L.call('b200sp_pool_lrn_bwd', dn1.data_ptr(), bf['p1'].data_ptr(), a1.data_ptr(), bf['am1'].data_ptr(), scratch.data_ptr(), da1.data_ptr(),
                B, g['H1'], g['W1'], 96, 1, LRN_ALPHA, LRN_BETA, 1, sp)
         self._conv_bwd(CONVS[0], da1, (B,) + self.HW, None, None)

@@ -36,7 +36,7 @@ def style_matrix(cov):
 
 
 class StyleAugmentor(torch.nn.Module):
-    def __init__(self, alpha, device, state=None):
+    def __init__(self, alpha, device, state=None, use_graph=True):
         """state: optional dict(ghiasi=state_dict, mean=[1,100], cov=[100,100] | A=[100,100], base=[100]) to bypass the
         checkpoint files (synthetic weights in tests / benchmarks)."""
         super().__init__()
@@ -54,6 +54,8 @@ class StyleAugmentor(torch.nn.Module):
         self.mean = state['mean'].float().reshape(-1).contiguous().to(self.device)
         self.imagenet_embedding = state['base'].float().reshape(-1).contiguous().to(self.device)   # SPEED+ mean, despite the name
         self._noise_host = None
+        self.use_graph = use_graph
+        self._graph = None            # (shape, graph, static x, static noise, static out)
 
     def sample_noise(self, n):
         """the reference draws on the CPU generator (styleAugmentor.py:47): same stream under torch.manual_seed"""
@@ -70,6 +72,9 @@ class StyleAugmentor(torch.nn.Module):
                float(self.alpha), e.data_ptr(), B, 100, L.stream_ptr())
         return e
 
+    def _run(self, x, noise, out=None):
+        return self.engine.forward(x, self.embed(noise), out=out)
+
     @torch.no_grad()
     def forward(self, x, noise=None):
         x = x.to(self.device).contiguous().float()
@@ -77,4 +82,25 @@ class StyleAugmentor(torch.nn.Module):
             noise = self.sample_noise(x.size(0))
         else:
             noise = noise.to(self.device).contiguous().float()
-        return self.engine.forward(x, self.embed(noise)).detach()
+        if not self.use_graph:
+            return self._run(x, noise).detach()
+        # the ~50 launches of a call are captured once per input shape; inputs go through static buffers
+        if self._graph is None or self._graph[0] != tuple(x.shape):
+            sx, sn = torch.empty_like(x), torch.empty_like(noise)
+            so = torch.empty_like(x)
+            sx.copy_(x); sn.copy_(noise)
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._run(sx, sn, so)                       # warm-up: allocates every plane / buffer
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._run(sx, sn, so)
+            self._graph = (tuple(x.shape), g, sx, sn, so)
+        _, g, sx, sn, so = self._graph
+        sx.copy_(x, non_blocking=True)
+        sn.copy_(noise, non_blocking=True)
+        g.replay()
+        return so.clone().detach()

@@ -109,7 +109,7 @@ def test_dann_step_within_fp32_noise_of_float64_oracle(B, alpha):
         assert rel(sdm[k], s64[k]) < 1e-3, k
     opt.step()
     torch.cuda.synchronize()
-    assert abs(opt.last_grad_norm() - gn) <= 3 * abs(r32['grad_norm'] - gn) + 1e-4 * gn
+    assert abs(opt.last_grad_norm() - gn) <= 3 * abs(r32['grad_norm'] - gn) + 1e-3 * gn
     sdm = m.state_dict()
     for k in ('domain_classifier.0.weight', 'net.head.0.weight', 'net.base.17.conv.2.weight'):
         e_cuda, e_f32 = rel(sdm[k], s64[k]), rel(s32[k], s64[k])
