@@ -23,6 +23,13 @@
 #include "tcgemm.cuh"
 #include "tc_common.cuh"
 
+#ifdef TCG_TIMELINE
+__device__ long long g_tcg_tl[8][256];
+#define TL(row, idx) do { if (blockIdx.x == 0 && (idx) < 256) g_tcg_tl[row][idx] = clock64(); } while (0)
+#else
+#define TL(row, idx) do {} while (0)
+#endif
+
 namespace {
 
 constexpr int EPI_T = 256, MMA_T = 32, PROD_T = 512;
@@ -427,7 +434,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
             if (fetch.valid()) { issue(fetch, d); fetch.next(g); }
             cp_async_commit();
         }
-        int rs = 0, os = 0;
+        int rs = 0, os = 0, tln = 0;
         uint32_t par = 1;
         while (cons.valid()) {
             if (cons.it != c_it) {
@@ -437,8 +444,11 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
             }
             LA.load_params(cons.kb);               // issued before the waits: their latency is hidden
             if (!g.b_res) LB.load_params(cons.kb);
+            if (pt == 0) TL(0, tln);
             if (g.n_raw == 4) cp_async_wait<3>(); else if (g.n_raw == 3) cp_async_wait<2>(); else cp_async_wait<1>();
+            if (pt == 0) TL(1, tln);
             mbar_wait_guard(&empty[os], par, g.wait_mode);
+            if (pt == 0) TL(2, tln);
             const uint32_t rbase = raw0 + rs * g.raw_stage_bytes;
             const uint32_t a_hi = s_base + os * g.op_stage_bytes, a_lo = a_hi + g.a_op_bytes;
             const uint32_t b_hi = a_hi + b_in_stage, b_lo = b_hi + g.b_op_bytes;
@@ -447,6 +457,8 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
             tc::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&full[os]);
+            if (pt == 0) TL(3, tln);
+            ++tln;
             // refill the raw slot just consumed with the k-block n_raw ahead
             if (fetch.valid()) { issue(fetch, rs); fetch.next(g); }
             cp_async_commit();
@@ -471,7 +483,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
         constexpr uint32_t B_HIW = ((BLAY == TCG_LAY_KM ? 1024u : SBO_MM) >> 4) | (1u << 14) | ((uint32_t)(BLAY == TCG_LAY_KM ? tc::SWZ_128B : LT_MM) << 29);
         auto mk = [](uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); };
         if (g.b_res) { mbar_wait_guard(bfull, 0, g.wait_mode); tc::tc_fence_after(); }
-        int os = 0, acc = 0;
+        int os = 0, acc = 0, tlm = 0;
         uint32_t fpar = 0, tpar = 1;
         for (int it = blockIdx.x; it < total; it += gridDim.x) {
             const Item w = get_item(g, it);
@@ -479,8 +491,10 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
             tc::tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * g.BN;
             for (int kb = w.kb0; kb < w.kb1; ++kb) {
+                if (lane == 0) TL(4, tlm);
                 mbar_wait_guard(&full[os], fpar, g.wait_mode);
                 tc::tc_fence_after();
+                if (lane == 0) TL(5, tlm);
                 if (lane == 0) {
                     const uint32_t a_hi = s_base + os * g.op_stage_bytes, a_lo = a_hi + g.a_op_bytes;
                     const uint32_t b_hi = g.b_res ? s_base + g.off_bres + kb * (E::NM * g.b_op_bytes) : a_hi + b_in_stage;
@@ -504,7 +518,9 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
                     }
                     tc::umma_commit(&empty[os]);
                     if (kb == w.kb1 - 1) tc::umma_commit(&tfull[acc]);
+                    TL(6, tlm);
                 }
+                ++tlm;
                 __syncwarp();
                 if (++os == g.n_op) { os = 0; fpar ^= 1; }
             }
@@ -841,3 +857,9 @@ int tcgemm_launch(const TcgProblem& p, cudaStream_t st) {
     if (p.dtype == B200SP_BF16) return launch_T<bf16>(a, p, st);
     return B200SP_ENOSYS;
 }
+
+#ifdef TCG_TIMELINE
+extern "C" int b200sp_tcg_timeline(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_tcg_tl, sizeof(long long) * 8 * 256);
+}
+#endif
