@@ -196,6 +196,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-out', default='')
     ap.add_argument('--no-secondary', action='store_true')
+    ap.add_argument('--dtype', default='fp32', choices=['fp32', 'bf16'], help='bf16 = the --use_fp16 path (secondary number; the headline is fp32)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -219,7 +220,7 @@ def main():
     W = max(3, args.warmup)
     K = max(1, args.steps)
 
-    model = KeypointRegressionNet(11, device=dev, seed=2021)
+    model = KeypointRegressionNet(11, device=dev, seed=2021, dtype=L.BF16 if args.dtype == 'bf16' else L.F32)
     model.train()
     opt = FusedAdamW(model._store, model.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
                      clip_mode=1, max_norm=1.0)
@@ -304,9 +305,10 @@ def main():
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'fp32', 'data': 'synthetic',
+            'dtype': args.dtype, 'data': 'synthetic',
             'config': {'workload': 'KRN train bs=48/GPU AdamW 224x224 synthetic (BASELINE.json configs[1])',
-                       'math': 'fp32 storage, 3xTF32 tensor-core GEMMs + fp32 CUDA-core stencils',
+                       'math': ('fp32 storage, 3xTF32 tensor-core GEMMs + fp32 CUDA-core stencils' if args.dtype == 'fp32' else
+                                'bf16 storage + bf16 tensor-core GEMMs, fp32 accumulate / statistics / master weights'),
                        'global_batch': world * BATCH, 'parallelism': 'dp%d' % world,
                        'cuda_graph': not args.no_graph,
                        'l2': 'per-step working set ~2.7 GB of activations >> 126 MB L2 (no explicit flush)'},

@@ -498,26 +498,28 @@ int dw_bwd_legacy(const b200sp_vtensor* dy, const b200sp_vtensor* x, const float
 
 extern "C" int b200sp_stem_fwd(const float* x_nchw, const float* w, void* y, const b200sp_bnfwd* bn,
                                int B, int H, int W, int dtype, void* stream) {
-    if (dtype != B200SP_F32) return B200SP_ENOSYS;
+    if (dtype != B200SP_F32 && dtype != B200SP_BF16) return B200SP_ENOSYS;
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     const long long npix = (long long)B * Ho * Wo;
     int grid = (int)((npix + 255) / 256);
     if (grid > NUM_SMS * 4) grid = NUM_SMS * 4;
     b200sp_bnfwd b = {};
     if (bn) b = *bn;
-    stem_fwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, w, (float*)y, b, bn != nullptr, B, H, W, Ho, Wo);
+    if (dtype == B200SP_F32) stem_fwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, w, (float*)y, b, bn != nullptr, B, H, W, Ho, Wo);
+    else stem_fwd_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, w, (bf16*)y, b, bn != nullptr, B, H, W, Ho, Wo);
     B200SP_COUNT_LAUNCH();
     B200SP_RETURN_LAST();
 }
 
 extern "C" int b200sp_stem_wgrad(const float* x_nchw, const b200sp_vtensor* dy, float* dw,
                                  int B, int H, int W, int dtype, void* stream) {
-    if (dtype != B200SP_F32) return B200SP_ENOSYS;
+    if (dtype != B200SP_F32 && dtype != B200SP_BF16) return B200SP_ENOSYS;
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     const long long npix = (long long)B * Ho * Wo;
     int grid = (int)((npix + 63) / 64);
     if (grid > NUM_SMS * 8) grid = NUM_SMS * 8;
-    stem_wgrad_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, *dy, dw, B, H, W, Ho, Wo);
+    if (dtype == B200SP_F32) stem_wgrad_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, *dy, dw, B, H, W, Ho, Wo);
+    else stem_wgrad_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, *dy, dw, B, H, W, Ho, Wo);
     B200SP_COUNT_LAUNCH();
     B200SP_RETURN_LAST();
 }

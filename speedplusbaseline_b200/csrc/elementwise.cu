@@ -294,11 +294,15 @@ inline int ew_grid(long long n) {
 
 extern "C" int b200sp_bn_apply(const void* y, const float* scale, const float* shift, const void* residual,
                                int act, void* out, int64_t M, int C, int dtype, void* stream) {
-    if (dtype != B200SP_F32) return B200SP_ENOSYS;
+    if (dtype != B200SP_F32 && dtype != B200SP_BF16) return B200SP_ENOSYS;
     if (C % 4) return B200SP_EINVAL;
     const long long n4 = M * (C / 4);
-    bn_apply_kernel<float><<<ew_grid(n4), EW_NT, 0, (cudaStream_t)stream>>>((const float*)y, scale, shift, (const float*)residual,
-                                                                          act, (float*)out, n4, C / 4);
+    if (dtype == B200SP_F32)
+        bn_apply_kernel<float><<<ew_grid(n4), EW_NT, 0, (cudaStream_t)stream>>>((const float*)y, scale, shift, (const float*)residual,
+                                                                              act, (float*)out, n4, C / 4);
+    else
+        bn_apply_kernel<bf16><<<ew_grid(n4), EW_NT, 0, (cudaStream_t)stream>>>((const bf16*)y, scale, shift, (const bf16*)residual,
+                                                                             act, (bf16*)out, n4, C / 4);
     B200SP_COUNT_LAUNCH();
     B200SP_RETURN_LAST();
 }
@@ -322,23 +326,25 @@ extern "C" int b200sp_bn_bwd_finalize(const b200sp_bnbwd* bn, int C, double coun
 }
 
 extern "C" int b200sp_bn_bwd_reduce(const void* g, const b200sp_bnbwd* bn, int64_t M, int C, int dtype, void* stream) {
-    if (dtype != B200SP_F32) return B200SP_ENOSYS;
+    if (dtype != B200SP_F32 && dtype != B200SP_BF16) return B200SP_ENOSYS;
     const int gy = ceil_div(C, 64);
     long long gx = (M + 3) / 4;
     const long long cap = (NUM_SMS * 8 + gy - 1) / gy;
     if (gx > cap) gx = cap;
-    bn_bwd_reduce_kernel<float><<<dim3((unsigned)gx, gy), EW_NT, 0, (cudaStream_t)stream>>>((const float*)g, *bn, M, C);
+    if (dtype == B200SP_F32) bn_bwd_reduce_kernel<float><<<dim3((unsigned)gx, gy), EW_NT, 0, (cudaStream_t)stream>>>((const float*)g, *bn, M, C);
+    else bn_bwd_reduce_kernel<bf16><<<dim3((unsigned)gx, gy), EW_NT, 0, (cudaStream_t)stream>>>((const bf16*)g, *bn, M, C);
     B200SP_COUNT_LAUNCH();
     B200SP_RETURN_LAST();
 }
 
 extern "C" int b200sp_colsum_f32(const b200sp_vtensor* dy, float* out, int M, int N, int dtype, void* stream) {
-    if (dtype != B200SP_F32) return B200SP_ENOSYS;
+    if (dtype != B200SP_F32 && dtype != B200SP_BF16) return B200SP_ENOSYS;
     const int gy = ceil_div(N, 64);
     long long gx = ((long long)M + 3) / 4;
     const long long cap = (NUM_SMS * 4 + gy - 1) / gy;
     if (gx > cap) gx = cap;
-    colsum_kernel<float><<<dim3((unsigned)gx, gy), EW_NT, 0, (cudaStream_t)stream>>>(*dy, out, M, N);
+    if (dtype == B200SP_F32) colsum_kernel<float><<<dim3((unsigned)gx, gy), EW_NT, 0, (cudaStream_t)stream>>>(*dy, out, M, N);
+    else colsum_kernel<bf16><<<dim3((unsigned)gx, gy), EW_NT, 0, (cudaStream_t)stream>>>(*dy, out, M, N);
     B200SP_COUNT_LAUNCH();
     B200SP_RETURN_LAST();
 }
@@ -351,21 +357,26 @@ extern "C" int b200sp_add_i64(int64_t* p, int64_t n, int64_t v, void* stream) {
 
 extern "C" int b200sp_reorg_cat_fwd(const b200sp_vtensor* xr, const b200sp_vtensor* x1, void* out,
                                     int B, int h, int w, int Cr, int C1, int dtype, void* stream) {
-    if (dtype != B200SP_F32) return B200SP_ENOSYS;
+    if (dtype != B200SP_F32 && dtype != B200SP_BF16) return B200SP_ENOSYS;
     if (Cr % 4 || C1 % 4) return B200SP_EINVAL;
     const long long n4 = (long long)B * h * w * ((4 * Cr + C1) / 4);
-    reorg_cat_fwd_kernel<float><<<ew_grid(n4), EW_NT, 0, (cudaStream_t)stream>>>(*xr, *x1, (float*)out, B, h, w, Cr, C1);
+    if (dtype == B200SP_F32) reorg_cat_fwd_kernel<float><<<ew_grid(n4), EW_NT, 0, (cudaStream_t)stream>>>(*xr, *x1, (float*)out, B, h, w, Cr, C1);
+    else reorg_cat_fwd_kernel<bf16><<<ew_grid(n4), EW_NT, 0, (cudaStream_t)stream>>>(*xr, *x1, (bf16*)out, B, h, w, Cr, C1);
     B200SP_COUNT_LAUNCH();
     B200SP_RETURN_LAST();
 }
 
 extern "C" int b200sp_reorg_cat_bwd(const void* dcat, void* g_r, void* g_1, const b200sp_bnbwd* bn_r,
                                     const b200sp_bnbwd* bn_1, int B, int h, int w, int Cr, int C1, int dtype, void* stream) {
-    if (dtype != B200SP_F32) return B200SP_ENOSYS;
+    if (dtype != B200SP_F32 && dtype != B200SP_BF16) return B200SP_ENOSYS;
     if (Cr % 4 || C1 % 4) return B200SP_EINVAL;
     const long long n4 = (long long)B * h * w * ((4 * Cr + C1) / 4);
-    reorg_cat_bwd_kernel<float><<<ew_grid(n4), EW_NT, 0, (cudaStream_t)stream>>>((const float*)dcat, (float*)g_r, (float*)g_1,
-                                                                               *bn_r, *bn_1, B, h, w, Cr, C1);
+    if (dtype == B200SP_F32)
+        reorg_cat_bwd_kernel<float><<<ew_grid(n4), EW_NT, 0, (cudaStream_t)stream>>>((const float*)dcat, (float*)g_r, (float*)g_1,
+                                                                                   *bn_r, *bn_1, B, h, w, Cr, C1);
+    else
+        reorg_cat_bwd_kernel<bf16><<<ew_grid(n4), EW_NT, 0, (cudaStream_t)stream>>>((const bf16*)dcat, (bf16*)g_r, (bf16*)g_1,
+                                                                                  *bn_r, *bn_1, B, h, w, Cr, C1);
     B200SP_COUNT_LAUNCH();
     if (int rc = b200sp_bn_bwd_reduce(g_r, bn_r, (int64_t)B * 4 * h * w, Cr, dtype, stream)) return rc;
     return b200sp_bn_bwd_reduce(g_1, bn_1, (int64_t)B * h * w, C1, dtype, stream);
@@ -379,9 +390,10 @@ extern "C" int b200sp_head_bias(const float* bias, float* logits, int B, int N, 
 
 extern "C" int b200sp_head_fwd(const b200sp_vtensor* x, const float* w, float* logits,
                                int B, int HWC, int C, int N, int dtype, void* stream) {
-    if (dtype != B200SP_F32) return B200SP_ENOSYS;
+    if (dtype != B200SP_F32 && dtype != B200SP_BF16) return B200SP_ENOSYS;
     if (N > HEAD_MAXN || x->mode == B200SP_VT_DY) return B200SP_EINVAL;
-    head_fwd_kernel<float><<<ceil_div(HWC, EW_NT), EW_NT, 0, (cudaStream_t)stream>>>(*x, w, logits, B, HWC, C, N);
+    if (dtype == B200SP_F32) head_fwd_kernel<float><<<ceil_div(HWC, EW_NT), EW_NT, 0, (cudaStream_t)stream>>>(*x, w, logits, B, HWC, C, N);
+    else head_fwd_kernel<bf16><<<ceil_div(HWC, EW_NT), EW_NT, 0, (cudaStream_t)stream>>>(*x, w, logits, B, HWC, C, N);
     B200SP_COUNT_LAUNCH();
     B200SP_RETURN_LAST();
 }
@@ -396,14 +408,18 @@ extern "C" int b200sp_krn_loss(const float* logits, const float* target, float* 
 
 extern "C" int b200sp_head_bwd(const float* dlogits, const b200sp_vtensor* x, const float* w, void* g, float* dw,
                                float* dbias, const b200sp_bnbwd* bn, int B, int HWC, int C, int N, int dtype, void* stream) {
-    if (dtype != B200SP_F32) return B200SP_ENOSYS;
+    if (dtype != B200SP_F32 && dtype != B200SP_BF16) return B200SP_ENOSYS;
     if (N > HEAD_MAXN || x->mode == B200SP_VT_DY) return B200SP_EINVAL;
     b200sp_bnbwd b = {};
     if (bn) b = *bn;
     const size_t smem = (size_t)B * HEAD_MAXN * sizeof(float);
     if (smem > 48 * 1024) return B200SP_EINVAL;
-    head_bwd_kernel<float><<<ceil_div(HWC, EW_NT), EW_NT, smem, (cudaStream_t)stream>>>(dlogits, *x, w, (float*)g, dw, dbias, b, bn != nullptr,
-                                                                                        B, HWC, C, N);
+    if (dtype == B200SP_F32)
+        head_bwd_kernel<float><<<ceil_div(HWC, EW_NT), EW_NT, smem, (cudaStream_t)stream>>>(dlogits, *x, w, (float*)g, dw, dbias, b, bn != nullptr,
+                                                                                            B, HWC, C, N);
+    else
+        head_bwd_kernel<bf16><<<ceil_div(HWC, EW_NT), EW_NT, smem, (cudaStream_t)stream>>>(dlogits, *x, w, (bf16*)g, dw, dbias, b, bn != nullptr,
+                                                                                           B, HWC, C, N);
     B200SP_COUNT_LAUNCH();
     if (bn && bn->s1) return b200sp_bn_bwd_finalize(bn, C, (double)B * (HWC / C), stream);
     B200SP_RETURN_LAST();

@@ -334,7 +334,7 @@ inline bool use_tc(int op, int M, int N, int K) {
 extern "C" int b200sp_pw_fwd(const b200sp_vtensor* x, const float* w, const float* bias, int out_act, void* y,
                              const b200sp_bnfwd* bn, int M, int N, int K, int dtype, void* stream) {
     if (!x || x->mode == B200SP_VT_DY) return B200SP_EINVAL;
-    if (use_tc(0, M, N, K) && dtype == B200SP_F32) {
+    if (dtype == B200SP_BF16 || use_tc(0, M, N, K)) {
         TcgProblem p = {};
         p.a = *x; p.b = plain_vt(w); p.a_lay = TCG_LAY_KM; p.b_lay = TCG_LAY_KM;
         p.P = M; p.Q = N; p.R = K; p.lda = K; p.ldb = K; p.epi = TCG_EPI_FWD; p.dtype = dtype;
@@ -357,7 +357,7 @@ extern "C" int b200sp_pw_fwd(const b200sp_vtensor* x, const float* w, const floa
 extern "C" int b200sp_pw_dgrad(const b200sp_vtensor* dy, const float* w, const void* skip, float scale_out, void* g,
                                const b200sp_bnbwd* bn, int M, int N, int K, int dtype, void* stream) {
     if (!dy) return B200SP_EINVAL;
-    if (use_tc(1, M, N, K) && dtype == B200SP_F32) {
+    if (dtype == B200SP_BF16 || use_tc(1, M, N, K)) {
         TcgProblem p = {};
         p.a = *dy; p.b = plain_vt(w); p.a_lay = TCG_LAY_KM; p.b_lay = TCG_LAY_MM;
         p.P = M; p.Q = K; p.R = N; p.lda = N; p.ldb = K; p.epi = TCG_EPI_DGRAD; p.dtype = dtype;
@@ -384,7 +384,7 @@ extern "C" int b200sp_pw_dgrad(const b200sp_vtensor* dy, const float* w, const v
 extern "C" int b200sp_pw_wgrad(const b200sp_vtensor* dy, const b200sp_vtensor* x, float* dw, float* dbias,
                                int M, int N, int K, int dtype, void* stream) {
     if (!dy || !x || x->mode == B200SP_VT_DY) return B200SP_EINVAL;
-    if (use_tc(2, M, N, K) && dtype == B200SP_F32) {
+    if (dtype == B200SP_BF16 || use_tc(2, M, N, K)) {
         TcgProblem p = {};
         p.a = *dy; p.b = *x; p.a_lay = TCG_LAY_MM; p.b_lay = TCG_LAY_MM;
         p.P = N; p.Q = K; p.R = M; p.lda = N; p.ldb = K; p.epi = TCG_EPI_ATOMIC; p.dtype = dtype;

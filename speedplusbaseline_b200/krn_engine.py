@@ -109,6 +109,12 @@ class KRNEngine:
         self.blocks = _blocks()
         self._ctxs = {}
         self.tdtype = torch.float32 if dtype == L.F32 else torch.bfloat16
+        import os
+        self._async_wgrad = os.environ.get('B200SP_ASYNC_WGRAD', '1') != '0'
+        self._side = torch.cuda.Stream(device=self.device) if self._async_wgrad else None
+        self._side_used = False
+        if dtype == L.BF16:
+            self.store.enable_lowp()
 
     # ------------------------------------------------------------------ helpers
     def ctx(self, B, slot=0):
@@ -167,11 +173,38 @@ class KRNEngine:
     def _wg(self, key):
         return self.store.wg_ptr(self.prefix + key)
 
+    def _wgrad(self, *args):
+        """b200sp_pw_wgrad on the side stream: a layer's weight gradient and its data gradient are independent
+        consumers of dY, and each of these GEMMs leaves most SMs idle (few tiles, latency-bound), so they overlap.
+        Fork after the kernel that produced dY (event), join at the end of backward().  Works under graph capture."""
+        if not self._async_wgrad:
+            L.call('b200sp_pw_wgrad', *args, L.stream_ptr())
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        self._side.wait_event(ev)
+        with torch.cuda.stream(self._side):
+            L.call('b200sp_pw_wgrad', *args, L.stream_ptr())
+        self._side_used = True
+
+    def _join_side(self):
+        if self._async_wgrad and self._side_used:
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+            torch.cuda.current_stream().wait_event(ev)
+            self._side_used = False
+
+    def _wq(self, key):
+        """GEMM weight operand in the activation dtype (bf16 mirror for --use_fp16, the fp32 master otherwise)."""
+        if self.dtype == L.BF16:
+            return self.store.wl_ptr(self.prefix + key)
+        return self.store.w_ptr(self.prefix + key)
+
     # ------------------------------------------------------------------ layer launchers
     def _pw_fwd(self, cx, xvt, wkey, bn_p, M, N, K, train, name, bias=None, out_act=L.ACT_NONE, shape=None):
         y = self._buf(cx.Y, name, shape)
         bn = self._bnfwd(cx, self._bi(bn_p), train) if bn_p else None
-        L.call('b200sp_pw_fwd', C.byref(xvt), self._w(wkey), bias, out_act, y.data_ptr(), bn, M, N, K, self.dtype, L.stream_ptr())
+        L.call('b200sp_pw_fwd', C.byref(xvt), self._wq(wkey), bias, out_act, y.data_ptr(), bn, M, N, K, self.dtype, L.stream_ptr())
         return y
 
     def _dw_fwd(self, cx, xvt, wkey, bn_p, B, H, W, Cc, stride, train, name):
@@ -286,10 +319,10 @@ class KRNEngine:
                    self._bnbwd(cx, bir, yr, L.ACT_LEAKY02), self._bnbwd(cx, bi1, yp1, L.ACT_RELU), B, h, w, 64, 1024, dt, sp)
             h13, w13 = cx.O[13].shape[1], cx.O[13].shape[2]
             dyr = self._vt_dy(cx, g_r, yr, bir)
-            L.call('b200sp_pw_wgrad', C.byref(dyr), C.byref(self._vt_plain(cx.O[13])), self._wg('extras.2.conv.0.weight'), None,
-                   B * h13 * w13, 64, 96, dt, sp)
+            self._wgrad(C.byref(dyr), C.byref(self._vt_plain(cx.O[13])), self._wg('extras.2.conv.0.weight'), None,
+                        B * h13 * w13, 64, 96, dt)
             d13p = self._buf(cx.dO, '13r', cx.O[13].shape)
-            L.call('b200sp_pw_dgrad', C.byref(dyr), self._w('extras.2.conv.0.weight'), None, 1.0, d13p.data_ptr(), None,
+            L.call('b200sp_pw_dgrad', C.byref(dyr), self._wq('extras.2.conv.0.weight'), None, 1.0, d13p.data_ptr(), None,
                    B * h13 * w13, 64, 96, dt, sp)
             # ---- extras.1, extras.0
             vt_e0 = self._vt_bnact(cx, cx.Y['xp0'], self._bi('extras.0.conv.4'), L.ACT_RELU)
@@ -313,9 +346,9 @@ class KRNEngine:
             yp, yd = cx.Y['p%d' % i], cx.Y['d%d' % i]
             dyp = self._vt_dy(cx, cx.dO[i], yp, bip)
             dvt = self._vt_bnact(cx, yd, bid, L.ACT_RELU6)
-            L.call('b200sp_pw_wgrad', C.byref(dyp), C.byref(dvt), self._wg('%s.%d.weight' % (p, j + 1)), None, Mo, cout, hid, dt, sp)
+            self._wgrad(C.byref(dyp), C.byref(dvt), self._wg('%s.%d.weight' % (p, j + 1)), None, Mo, cout, hid, dt)
             gd = self._buf(cx.G, 'd%d' % i, yd.shape)
-            L.call('b200sp_pw_dgrad', C.byref(dyp), self._w('%s.%d.weight' % (p, j + 1)), None, 1.0, gd.data_ptr(),
+            L.call('b200sp_pw_dgrad', C.byref(dyp), self._wq('%s.%d.weight' % (p, j + 1)), None, 1.0, gd.data_ptr(),
                    self._bnbwd(cx, bid, yd, L.ACT_RELU6), Mo, cout, hid, dt, sp)
             dyd = self._vt_dy(cx, gd, yd, bid)
             if t != 1:
@@ -326,14 +359,14 @@ class KRNEngine:
                        self._wg('%s.%d.0.weight' % (p, j)), self._bnbwd(cx, bie, ye, L.ACT_RELU6), B, hi_, wi_, hid, s, dt, sp)
                 dye = self._vt_dy(cx, ge, ye, bie)
                 xin = cx.O[i - 1]
-                L.call('b200sp_pw_wgrad', C.byref(dye), C.byref(self._vt_plain(xin)), self._wg(p + '.0.0.weight'), None, Mi, hid, cin, dt, sp)
+                self._wgrad(C.byref(dye), C.byref(self._vt_plain(xin)), self._wg(p + '.0.0.weight'), None, Mi, hid, cin, dt)
                 # gradient wrt the block input = dgrad (+ residual skip) (+ RouterV2 branch for base[13])
                 skip = cx.dO[i] if b['res'] else (cx.dO['13r'] if (i == 14 and pose) else None)
                 dprev = self._buf(cx.dO, i - 1, xin.shape)
                 pprev = 'base.%d.conv' % (i - 1)
                 tprev = self.blocks[i - 2]['t']
                 biprev = self._bi('%s.%d' % (pprev, 2 if tprev == 1 else 3))
-                L.call('b200sp_pw_dgrad', C.byref(dye), self._w(p + '.0.0.weight'), skip.data_ptr() if skip is not None else None, 1.0,
+                L.call('b200sp_pw_dgrad', C.byref(dye), self._wq(p + '.0.0.weight'), skip.data_ptr() if skip is not None else None, 1.0,
                        dprev.data_ptr(), self._bnbwd(cx, biprev, cx.Y['p%d' % (i - 1)], L.ACT_NONE), Mi, hid, cin, dt, sp)
             else:
                 # block 1: depthwise reads the stem activation directly
@@ -344,6 +377,7 @@ class KRNEngine:
                        self._wg('%s.0.0.weight' % p), self._bnbwd(cx, bi0, y0, L.ACT_RELU6), B, hi_, wi_, hid, s, dt, sp)
                 dy0 = self._vt_dy(cx, g0, y0, bi0)
                 L.call('b200sp_stem_wgrad', cx.images.data_ptr(), C.byref(dy0), self._wg('base.0.0.weight'), B, cx.H, cx.W, dt, sp)
+        self._join_side()
 
     # ------------------------------------------------------------------ DANN domain classifier
     def domain_forward(self, cx, label, loss_slot=0):
@@ -397,9 +431,9 @@ class KRNEngine:
         bip, bid = self._bi(p + '.4'), self._bi(p + '.1')
         dyp = self._vt_dy(cx, cx.G['xp%d' % e], yp, bip)
         dvt = self._vt_bnact(cx, yd, bid, L.ACT_RELU)
-        L.call('b200sp_pw_wgrad', C.byref(dyp), C.byref(dvt), self._wg(p + '.3.weight'), None, M, cout, cin, dt, sp)
+        self._wgrad(C.byref(dyp), C.byref(dvt), self._wg(p + '.3.weight'), None, M, cout, cin, dt)
         gd = self._buf(cx.G, 'xd%d' % e, yd.shape)
-        L.call('b200sp_pw_dgrad', C.byref(dyp), self._w(p + '.3.weight'), None, 1.0, gd.data_ptr(),
+        L.call('b200sp_pw_dgrad', C.byref(dyp), self._wq(p + '.3.weight'), None, 1.0, gd.data_ptr(),
                self._bnbwd(cx, bid, yd, L.ACT_RELU), M, cout, cin, dt, sp)
         dyd = self._vt_dy(cx, gd, yd, bid)
         L.call('b200sp_dw_bwd', C.byref(dyd), C.byref(in_vt), self._w(p + '.0.weight'), skip.data_ptr() if skip is not None else None,

@@ -60,7 +60,7 @@ class FusedAdamW(torch.optim.Optimizer):
         if self.clip_mode == 1:
             L.call('b200sp_grad_sqnorm', st.grads.data_ptr(), st.n, hp, sp)
         L.call('b200sp_adamw_step', st.params.data_ptr(), st.grads.data_ptr(), self.exp_avg.data_ptr(),
-               self.exp_avg_sq.data_ptr(), None, st.n, hp, sp)
+               self.exp_avg_sq.data_ptr(), st.params_lowp.data_ptr() if getattr(st, 'params_lowp', None) is not None else None, st.n, hp, sp)
         self._step_host += 1
 
     def zero_grad(self, set_to_none=True):

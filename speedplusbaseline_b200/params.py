@@ -20,6 +20,10 @@ def _align4(n):
     return (n + 3) // 4 * 4
 
 
+def _align8(n):       # segment starts: 16-byte aligned in fp32 AND in the bf16 mirror
+    return (n + 7) // 8 * 8
+
+
 class Entry:
     __slots__ = ('key', 'kind', 'ref_shape', 'numel', 'off')
 
@@ -82,7 +86,7 @@ class ParamStore:
         for key, kind, shp in weights:
             e = Entry(key, kind, shp)
             e.off = off
-            off = _align4(off + e.numel)
+            off = _align8(off + e.numel)
             self.entries[key] = e
         self.bns = list(bns)
         self.bn_index = {p: i for i, (p, _) in enumerate(self.bns)}
@@ -90,7 +94,7 @@ class ParamStore:
         c = 0
         for _, C in self.bns:
             self.bn_off.append(c)
-            c += _align4(C)
+            c += _align8(C)
         self.totC = c
         self.gamma_off = off
         self.beta_off = off + self.totC
@@ -101,6 +105,17 @@ class ParamStore:
         self.bufs[self.totC:] = 1.0
         self.nbt = torch.zeros(max(1, len(self.bns)), dtype=torch.int64, device=device)
         self.params[self.gamma_off:self.gamma_off + self.totC] = 1.0
+        self.params_lowp = None          # bf16 mirror of `params` (GEMM weights of the --use_fp16 path), see enable_lowp()
+
+    def enable_lowp(self):
+        """allocate / refresh the bf16 mirror; the fused AdamW keeps it current afterwards (b200sp_adamw_step p_lowp)."""
+        if self.params_lowp is None:
+            self.params_lowp = torch.empty(self.n, dtype=torch.bfloat16, device=self.device)
+        self.params_lowp.copy_(self.params)
+        return self.params_lowp
+
+    def wl_ptr(self, key):
+        return self.params_lowp.data_ptr() + 2 * self.entries[key].off
 
     # ---- pointers ---------------------------------------------------------------------------
     def p_ptr(self, off):
@@ -191,6 +206,8 @@ class ParamStore:
                         self.bufs[rv].copy_(v)
                     else:
                         self.nbt[r[1]] = int(v)
+            if self.params_lowp is not None:
+                self.params_lowp.copy_(self.params)
         return missing, unexpected
 
     def grad_dict(self):
