@@ -10,7 +10,7 @@ from . import _build
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_RELU6, ACT_LEAKY02, ACT_SIGMOID = 0, 1, 2, 3, 4
 VT_PLAIN, VT_BNACT, VT_DY = 0, 1, 2
-BF16_ENABLED = False      # bf16 activation storage (--use_fp16): kernels templated, entry points not opened yet
+BF16_ENABLED = os.environ.get('B200SP_ENABLE_BF16', '0') == '1'   # experimental bf16 storage for --use_fp16
 
 vp = C.c_void_p
 
