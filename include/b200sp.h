@@ -233,6 +233,11 @@ int b200sp_gemm_dgrad(const b200sp_vtensor *dy, int lddy, const float *w, const 
 int b200sp_gemm_wgrad(const b200sp_vtensor *dy, int lddy, const b200sp_vtensor *x, int ldx, float *dw,
                       int M, int N, int K, int dtype, void *stream);
 int b200sp_colsum_f32(const b200sp_vtensor *dy, float *out /* += */, int M, int N, int dtype, void *stream);
+/* split-K FC layers for M <= 128 rows (spn.py:80-99): y_acc[M,N] += X[M,K] W[N,K]^T ; dx_acc[M,K] += dY[M,N] W[N,K]
+ * (fp32 red.add: y_acc must be zero, dx_acc zero or the gradient to accumulate onto); b200sp_bias_act finishes the forward */
+int b200sp_fc_fwd_splitk(const float *x, const float *w, float *y_acc, int M, int N, int K, void *stream);
+int b200sp_fc_dgrad_splitk(const float *dy, const float *w, float *dx_acc, int M, int N, int K, void *stream);
+int b200sp_bias_act(float *y, const float *bias, int M, int N, int relu, void *stream);
 /* patch matrix of a k x k / stride / zero-pad convolution over channels [c_off, c_off+Cg) of x ([B,H,W,C] NHWC, or the
  * loader's NCHW image when nchw != 0): col[B*Ho*Wo][Kp], column (kh*k+kw)*Cg + c, zero-padded to Kp columns */
 int b200sp_im2col(const float *x, float *col, int B, int H, int W, int C, int c_off, int Cg, int k, int stride, int pad,

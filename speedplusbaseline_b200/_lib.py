@@ -105,6 +105,9 @@ _SIGS = {
     'b200sp_gemm_dgrad': ([PVT, i32, vp, vp, f32, vp, PBB, i32, i32, i32, i32, vp], i32),
     'b200sp_gemm_wgrad': ([PVT, i32, PVT, i32, vp, i32, i32, i32, i32, vp], i32),
     'b200sp_colsum_f32': ([PVT, vp, i32, i32, i32, vp], i32),
+    'b200sp_fc_fwd_splitk': ([vp, vp, vp, i32, i32, i32, vp], i32),
+    'b200sp_fc_dgrad_splitk': ([vp, vp, vp, i32, i32, i32, vp], i32),
+    'b200sp_bias_act': ([vp, vp, i32, i32, i32, vp], i32),
     'b200sp_im2col': ([vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp], i32),
     'b200sp_col2im': ([vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp], i32),
     'b200sp_pool_lrn_fwd': ([vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp], i32),

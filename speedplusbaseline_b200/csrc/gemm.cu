@@ -444,3 +444,22 @@ extern "C" int b200sp_gemm_wgrad(const b200sp_vtensor* dy, int lddy, const b200s
     p.out = dw;
     return tcgemm_launch(p, (cudaStream_t)stream);
 }
+
+// ---- split-K FC layers (M <= 128 rows: SPN fc6-fc11, src/nets/spn.py:80-99) ------------------------------------------
+// With a single 128-row M tile the K loop (K/8 x 3 tcgen05.mma, ~115 cycles each) is the whole critical path of a CTA;
+// splitting it across CTAs and reducing with fp32 red.add turns 267 us into ~50 us for fc6.  The output must be
+// zero (fwd) or hold the value to accumulate onto (dgrad: the other branch's gradient) on entry.
+extern "C" int b200sp_fc_fwd_splitk(const float* x, const float* w, float* y_acc, int M, int N, int K, void* stream) {
+    TcgProblem p = {};
+    p.a = plain_vt(x); p.b = plain_vt(w); p.a_lay = TCG_LAY_KM; p.b_lay = TCG_LAY_KM;
+    p.P = M; p.Q = N; p.R = K; p.lda = K; p.ldb = K; p.epi = TCG_EPI_ATOMIC; p.dtype = B200SP_F32;
+    p.out = y_acc;
+    return tcgemm_launch(p, (cudaStream_t)stream);
+}
+extern "C" int b200sp_fc_dgrad_splitk(const float* dy, const float* w, float* dx_acc, int M, int N, int K, void* stream) {
+    TcgProblem p = {};
+    p.a = plain_vt(dy); p.b = plain_vt(w); p.a_lay = TCG_LAY_KM; p.b_lay = TCG_LAY_MM;
+    p.P = M; p.Q = K; p.R = N; p.lda = N; p.ldb = K; p.epi = TCG_EPI_ATOMIC; p.dtype = B200SP_F32;
+    p.out = dx_acc;
+    return tcgemm_launch(p, (cudaStream_t)stream);
+}

@@ -228,6 +228,17 @@ __global__ void soft_ce_mean_kernel(const float* __restrict__ rows_c, const floa
     }
 }
 
+// y = act(y + bias[n]) in place (the epilogue of a split-K FC forward)
+__global__ void __launch_bounds__(SP_NT) bias_act_kernel(float* __restrict__ y, const float* __restrict__ bias, long long n4, int N4, int relu) {
+    for (long long i = (long long)blockIdx.x * SP_NT + threadIdx.x; i < n4; i += (long long)gridDim.x * SP_NT) {
+        float4 v = *reinterpret_cast<float4*>(y + i * 4);
+        const float4 b = ldg4(bias + (i % N4) * 4);
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        *reinterpret_cast<float4*>(y + i * 4) = v;
+    }
+}
+
 __global__ void __launch_bounds__(SP_NT) relu_mask_kernel(float* __restrict__ g, const float* __restrict__ a, long long n) {
     for (long long i = (long long)blockIdx.x * SP_NT + threadIdx.x; i < n; i += (long long)gridDim.x * SP_NT)
         if (!(a[i] > 0.f)) g[i] = 0.f;
@@ -303,6 +314,14 @@ extern "C" int b200sp_soft_ce_mean(const float* rows_c, const float* rows_r, flo
 
 extern "C" int b200sp_relu_mask(float* g, const float* a, int64_t n, void* stream) {
     relu_mask_kernel<<<sp_grid(n), SP_NT, 0, (cudaStream_t)stream>>>(g, a, n);
+    B200SP_COUNT_LAUNCH();
+    B200SP_RETURN_LAST();
+}
+
+extern "C" int b200sp_bias_act(float* y, const float* bias, int M, int N, int relu, void* stream) {
+    if (N % 4) return B200SP_EINVAL;
+    const long long n4 = (long long)M * (N / 4);
+    bias_act_kernel<<<sp_grid(n4), SP_NT, 0, (cudaStream_t)stream>>>(y, bias, n4, N / 4, relu);
     B200SP_COUNT_LAUNCH();
     B200SP_RETURN_LAST();
 }

@@ -816,6 +816,12 @@ int launch_T(TcgArgs& a, const TcgProblem& p, cudaStream_t st) {
         if (am == B200SP_VT_PLAIN) return launch_cfg<T, TCG_LAY_KM, TCG_LAY_MM, TCG_EPI_DGRAD, XM_PLAIN, XM_PLAIN>(a, st);
         if (am == B200SP_VT_DY) return launch_cfg<T, TCG_LAY_KM, TCG_LAY_MM, TCG_EPI_DGRAD, XM_DY, XM_PLAIN>(a, st);
     }
+    // split-K GEMMs with a plain fp32 red.add epilogue over K-major / mixed operands: the M <= 128 FC layers of the SPN
+    // (one M tile: the K loop is the whole critical path, so it is split across CTAs)
+    if (p.epi == TCG_EPI_ATOMIC && p.a_lay == TCG_LAY_KM && am == B200SP_VT_PLAIN && bm == B200SP_VT_PLAIN) {
+        if (p.b_lay == TCG_LAY_KM) return launch_cfg<T, TCG_LAY_KM, TCG_LAY_KM, TCG_EPI_ATOMIC, XM_PLAIN, XM_PLAIN>(a, st);
+        return launch_cfg<T, TCG_LAY_KM, TCG_LAY_MM, TCG_EPI_ATOMIC, XM_PLAIN, XM_PLAIN>(a, st);
+    }
     if (p.epi == TCG_EPI_ATOMIC && p.a_lay == TCG_LAY_MM && p.b_lay == TCG_LAY_MM) {
         if (am == B200SP_VT_PLAIN && bm == B200SP_VT_PLAIN) return launch_cfg<T, TCG_LAY_MM, TCG_LAY_MM, TCG_EPI_ATOMIC, XM_PLAIN, XM_PLAIN>(a, st);
         if (am == B200SP_VT_PLAIN && bm == B200SP_VT_BNACT) return launch_cfg<T, TCG_LAY_MM, TCG_LAY_MM, TCG_EPI_ATOMIC, XM_PLAIN, XM_BNACT>(a, st);

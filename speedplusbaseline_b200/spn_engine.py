@@ -109,10 +109,16 @@ class SPNEngine:
     # ------------------------------------------------------------------ FC
     def _fc_fwd(self, name, x, B, K, N, act, tag):
         y = self._buf('h_' + tag, (B, N))
+        sp = L.stream_ptr()
+        if B <= 128:        # one M tile: split the K loop across CTAs (fp32 red.add), bias + ReLU in a tiny second pass
+            y.zero_()
+            L.call('b200sp_fc_fwd_splitk', x.data_ptr(), self.store.w_ptr(name + '.weight'), y.data_ptr(), B, N, K, sp)
+            L.call('b200sp_bias_act', y.data_ptr(), self.store.w_ptr(name + '.bias'), B, N, 1 if act == L.ACT_RELU else 0, sp)
+            return y
         vt = self._vt(x.data_ptr())
         self.keep.append(vt)
         L.call('b200sp_pw_fwd', C.byref(vt), self.store.w_ptr(name + '.weight'), self.store.w_ptr(name + '.bias'), act, y.data_ptr(), None,
-               B, N, K, L.F32, L.stream_ptr())
+               B, N, K, L.F32, sp)
         return y
 
     def _fc_bwd(self, name, dy, x, B, K, N, dx, skip, mask_y):
@@ -120,6 +126,15 @@ class SPNEngine:
         vdy, vx = self._vt(dy.data_ptr()), self._vt(x.data_ptr())
         self.keep += [vdy, vx]
         L.call('b200sp_pw_wgrad', C.byref(vdy), C.byref(vx), st.wg_ptr(name + '.weight'), st.wg_ptr(name + '.bias'), B, N, K, L.F32, sp)
+        if B <= 128:
+            if skip is None:
+                dx.zero_()
+            else:
+                assert skip.data_ptr() == dx.data_ptr()          # accumulate onto the other branch's gradient in place
+            L.call('b200sp_fc_dgrad_splitk', dy.data_ptr(), st.w_ptr(name + '.weight'), dx.data_ptr(), B, N, K, sp)
+            if mask_y is not None:
+                L.call('b200sp_relu_mask', dx.data_ptr(), mask_y.data_ptr(), dx.numel(), sp)
+            return
         L.call('b200sp_pw_dgrad', C.byref(vdy), st.w_ptr(name + '.weight'), skip.data_ptr() if skip is not None else None, 1.0, dx.data_ptr(),
                self._mask_bn(mask_y) if mask_y is not None else None, B, N, K, L.F32, sp)
 
