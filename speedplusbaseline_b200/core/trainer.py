@@ -109,11 +109,9 @@ def train_single_epoch_krn(epoch, cfg, model, data_loader, optimizer,
         stepper = KRNTrainStep(model, optimizer, use_graph=getattr(cfg, 'use_graph', True))
         model._train_step = stepper
     pending = None
-    for idx, (images, target) in enumerate(data_loader):
+    for idx, (images, target) in enumerate(DevicePrefetcher(data_loader, device)):
         start = time.time()
         B = images.shape[0]
-        images = images.to(device, non_blocking=True).float().contiguous()
-        target = target.to(device, non_blocking=True).float().contiguous()
         if styleAugmentor is not None and random.random() < cfg.texture_ratio:
             images = styleAugmentor(images)
         loss3 = stepper.step(images, target)
@@ -137,6 +135,62 @@ def train_single_epoch_krn(epoch, cfg, model, data_loader, optimizer,
     if writer is not None:
         writer.add_scalar('train/loss_x', loss_x_meter.avg, epoch)
         writer.add_scalar('train/loss_y', loss_y_meter.avg, epoch)
+
+
+class DevicePrefetcher:
+    """Wraps a loader of pinned HOST batches: the host->device copy of batch i+1 runs on a copy stream while the
+    GPU computes batch i (the reference copies synchronously in the loop, trainer.py:64-65).  Two device buffer sets;
+    a buffer is refilled only after the step that consumed it has been enqueued (event), so nothing is overwritten
+    early.  Yields tuples of device tensors valid until the next-but-one iteration."""
+
+    def __init__(self, loader, device):
+        self.loader, self.device = loader, device
+        self.stream = torch.cuda.Stream(device=device)
+        self.bufs = [None, None]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.consumed = [None, None]
+
+    def __len__(self):
+        return len(self.loader)
+
+    def _issue(self, slot, batch):
+        batch = batch if isinstance(batch, (tuple, list)) else (batch,)
+        if self.bufs[slot] is None or any(tuple(b.shape) != tuple(t.shape) for b, t in zip(self.bufs[slot], batch)):
+            self.bufs[slot] = [torch.empty(t.shape, dtype=torch.float32, device=self.device) for t in batch]
+        if self.consumed[slot] is not None:
+            self.stream.wait_event(self.consumed[slot])
+        with torch.cuda.stream(self.stream):
+            for b, t in zip(self.bufs[slot], batch):
+                b.copy_(t, non_blocking=True)
+            self.ready[slot].record(self.stream)
+
+    def mark_consumed(self, slot):
+        ev = torch.cuda.Event()
+        ev.record()
+        self.consumed[slot] = ev
+
+    def __iter__(self):
+        it = iter(self.loader)
+        try:
+            nxt = next(it)
+        except StopIteration:
+            return
+        slot = 0
+        self._issue(slot, nxt)
+        while True:
+            torch.cuda.current_stream().wait_event(self.ready[slot])
+            cur, cur_slot = self.bufs[slot], slot
+            try:
+                nxt = next(it)
+                self._issue(slot ^ 1, nxt)
+                more = True
+            except StopIteration:
+                more = False
+            yield tuple(cur)
+            self.mark_consumed(cur_slot)        # the consumer has enqueued its work on the current stream
+            if not more:
+                return
+            slot ^= 1
 
 
 class SPNTrainStep:
