@@ -193,6 +193,11 @@ typedef struct b200sp_convtc_desc {
 } b200sp_convtc_desc;
 int b200sp_convtc_fwd(const b200sp_convtc_desc *d, void *stream);
 
+/* second half of a row-decomposed k x k convolution with Co <= 4 outputs (ghiasi.py:121): T [B][Ho][Wq][Nt] holds, per
+ * plane-grid pixel, the k*Co partial sums over (kh, c) computed by b200sp_convtc_fwd with k row-shift taps;
+ * out[b,h,w,co] = sum_kw T[b,h,w+kw][kw*Co+co] (fp32 [B][Ho][Wo][N_out]) and stats [B][2][N_pad] += per-image sum / sum^2 */
+int b200sp_conv_kwsum(const float *T, float *out, float *stats, int B, int Ho, int Wo, int Wq, int Nt, int k, int Co, int N_out,
+                      int N_pad, void *stream);
 /* NCHW fp32 image [B,3,H,W] -> reflection-padded NHWC bf16 plane [B][H+2p][W+2p][Cd] (channels >= 3 zero) */
 int b200sp_sa_prep(const float *x_nchw, void *plane, int B, int H, int W, int pad, int Cd, void *stream);
 /* InstanceNorm2d(affine=False, eps) statistics -> per-(image, channel) scale/shift, folding the conditional

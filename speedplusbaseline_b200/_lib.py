@@ -95,6 +95,7 @@ _SIGS = {
     'b200sp_krn_loss': ([vp, vp, vp, vp, vp, vp, i32, i32, vp], i32),
     'b200sp_head_bwd': ([vp, PVT, vp, vp, vp, vp, PBB, i32, i32, i32, i32, i32, vp], i32),
     'b200sp_convtc_fwd': ([C.POINTER(ConvDesc), vp], i32),
+    'b200sp_conv_kwsum': ([vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp], i32),
     'b200sp_sa_prep': ([vp, vp, i32, i32, i32, i32, i32, vp], i32),
     'b200sp_in_finalize': ([vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, f32, vp], i32),
     'b200sp_in_apply': ([C.POINTER(InApplyDesc), vp], i32),

@@ -117,6 +117,42 @@ __global__ void __launch_bounds__(SA_NT) in_apply_final_kernel(const float* __re
     }
 }
 
+// Row-decomposed 9x9 (k x k) convolution with very few output channels (ghiasi.py:121, 32 -> 3): the tensor-core
+// pass computes, for every plane-grid pixel m', T[m'][kw*Co + co] = sum_{kh,c} in[m' + kh*Wq][c] w[co][c][kh][kw]
+// (k taps instead of k*k: the operand traffic that bounds this layer drops k-fold, and N = k*Co fills the MMA
+// instead of 3 of 16 columns); this kernel finishes  out[b,h,w,co] = sum_kw T[(b,h,w+kw)][kw*Co + co]  and
+// accumulates the InstanceNorm sums.  One thread per output pixel; T rows are re-read from L1/L2.
+__global__ void __launch_bounds__(SA_NT) kwsum_kernel(const float* __restrict__ T, float* __restrict__ out, float* __restrict__ stats,
+                                                     int B, int Ho, int Wo, int Wq, int Nt, int k, int Co, int No, int Np) {
+    __shared__ float s_sum[8], s_sq[8];
+    const int b = blockIdx.y;
+    if (threadIdx.x < 8) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
+    __syncthreads();
+    float ls[4] = {0.f, 0.f, 0.f, 0.f}, lq[4] = {0.f, 0.f, 0.f, 0.f};
+    const int npix = Ho * Wo;
+    for (int i = blockIdx.x * SA_NT + threadIdx.x; i < npix; i += gridDim.x * SA_NT) {
+        const int h = i / Wo, w = i - h * Wo;
+        const float* t = T + ((size_t)(b * Ho + h) * Wq + w) * Nt;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int kw = 0; kw < k; ++kw)
+            for (int co = 0; co < Co; ++co) acc[co] += __ldg(t + (size_t)kw * Nt + kw * Co + co);
+        float* o = out + ((size_t)b * npix + i) * No;
+        for (int co = 0; co < No; ++co) o[co] = co < Co ? acc[co] : 0.f;
+        for (int co = 0; co < Co; ++co) { ls[co] += acc[co]; lq[co] = fmaf(acc[co], acc[co], lq[co]); }
+    }
+    for (int co = 0; co < Co; ++co) {
+        float a = ls[co], q = lq[co];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&s_sum[co], a); atomicAdd(&s_sq[co], q); }
+    }
+    __syncthreads();
+    if (threadIdx.x < Co) {
+        atomicAdd(stats + (size_t)b * 2 * Np + threadIdx.x, s_sum[threadIdx.x]);
+        atomicAdd(stats + (size_t)b * 2 * Np + Np + threadIdx.x, s_sq[threadIdx.x]);
+    }
+}
+
 __global__ void __launch_bounds__(SA_NT) style_embed_kernel(const float* __restrict__ noise, const float* __restrict__ A,
                                                             const float* __restrict__ mean, const float* __restrict__ base, float alpha,
                                                             float* __restrict__ out, int B, int D) {
@@ -188,6 +224,16 @@ extern "C" int b200sp_style_embed(const float* noise, const float* A, const floa
 
 extern "C" int b200sp_style_linear(const float* emb, const float* W, const float* bias, float* out, int B, int D, int T, void* stream) {
     style_linear_kernel<<<ceil_div((long long)B * T, SA_NT), SA_NT, 0, (cudaStream_t)stream>>>(emb, W, bias, out, B, D, T);
+    B200SP_COUNT_LAUNCH();
+    B200SP_RETURN_LAST();
+}
+
+extern "C" int b200sp_conv_kwsum(const float* T, float* out, float* stats, int B, int Ho, int Wo, int Wq, int Nt, int k, int Co, int N_out,
+                                 int N_pad, void* stream) {
+    if (Co > 4 || N_out > 4 || k * Co > Nt) return B200SP_EINVAL;
+    int gx = ceil_div((long long)Ho * Wo, SA_NT);
+    if (gx > 64) gx = 64;
+    kwsum_kernel<<<dim3(gx, B), SA_NT, 0, (cudaStream_t)stream>>>(T, out, stats, B, Ho, Wo, Wq, Nt, k, Co, N_out, N_pad);
     B200SP_COUNT_LAUNCH();
     B200SP_RETURN_LAST();
 }

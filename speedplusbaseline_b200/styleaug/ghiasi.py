@@ -100,6 +100,47 @@ class _Conv:
         return d
 
 
+class _RowConv:
+    """k x k stride-1 convolution with <= 4 output channels as a k-tap shifted GEMM producing T[m'][kw*Co + co]
+    (see b200sp_conv_kwsum): the tensor-core pass has k taps instead of k*k and N = k*Co instead of Co."""
+
+    def __init__(self, name, w, Cp, device):
+        self.name, self.k, self.Cp, self.device = name, w.shape[2], Cp, device
+        self.Co, self.Ci = w.shape[0], w.shape[1]
+        self.Nt = (self.k * self.Co + 15) // 16 * 16          # MMA N
+        self.N_pad = 16                                       # stats row width of the finished conv
+        self.N_out = 4
+        self.w_ref = w
+        self._geo = None
+
+    def setup(self, B, Hq, Wq, Ho, planes, T):
+        geo = (B, Hq, Wq, Ho)
+        k, Co, Ci, Cp = self.k, self.Co, self.Ci, self.Cp
+        cbox = min(Cp, 64)
+        P = 64 // cbox
+        assert Cp <= 64
+        if self._geo != geo:
+            # chunk kh: plane rows m' + kh*Wq, first pixel of the 128-byte row only (the other P-1 pixels meet zero weights)
+            m = torch.zeros(self.Nt, 64 * k, dtype=torch.float32)
+            wr = self.w_ref.float().cpu()
+            for kh in range(k):
+                for kw in range(k):
+                    for co in range(Co):
+                        m[kw * Co + co, kh * 64:kh * 64 + Ci] = wr[co, :, kh, kw]
+            self.wp = m.to(torch.bfloat16).contiguous().to(self.device)
+            self.chunks = [(0, 0, kh * Wq) for kh in range(k)]
+            self._geo = geo
+        d = L.ConvDesc()
+        for i in range(4):
+            d.planes[i] = planes[i].data_ptr() if i < len(planes) else None
+        d.w, d.out, d.stats = self.wp.data_ptr(), T.data_ptr(), None
+        d.C, d.B, d.Hq, d.Wq, d.Ho, d.Wo = Cp, B, Hq, Wq, Ho, Wq      # every plane column of the first Ho rows is a valid T row
+        d.N_pad, d.N_out, d.n_chunks = self.Nt, self.Nt, k
+        for j, (pl, c0, sh) in enumerate(self.chunks):
+            d.chunks[j].plane, d.chunks[j].c0, d.chunks[j].shift = pl, c0, sh
+        return d
+
+
 class GhiasiEngine:
     def __init__(self, state_dict, device):
         L.require_cuda()
@@ -120,6 +161,8 @@ class GhiasiEngine:
         add('c8', 'layers.8.conv.weight', 3, 1, 128)
         add('c9', 'layers.9.conv.weight', 3, 1, 64)
         add('c10', 'layers.10.conv.weight', 9, 1, 32)
+        self.c10_row = _RowConv('c10row', sd['layers.10.conv.weight'], 32, dev)
+        self.row_decomposed_c10 = True
         # the 26 Linear(100 -> C) of the conditional instance norms, concatenated: per set [gamma | beta]
         Ws, bs, self.gb_off, off = [], [], {}, 0
         for p, sfx, Cc in cond_sets():
@@ -238,7 +281,18 @@ class GhiasiEngine:
         sc, sh = self._finalize(st, cv, B, H * W, gb, ('layers.9', ''))
         pl, Hd, Wd = self._apply(raw, sc, sh, B, H, W, 32, L.ACT_RELU, 4, 1, 1, 'p10')
         # layer 10: 9x9 32->3, cond IN, sigmoid
-        raw, st, cv = self._conv('c10', pl, B, Hd, Wd, H, W)
+        if self.row_decomposed_c10:
+            rc = self.c10_row
+            T = self._buf('T10', (B, H, Wd, rc.Nt), torch.float32)
+            d = rc.setup(B, Hd, Wd, H, pl, T)
+            self._keep.append(d)
+            L.call('b200sp_convtc_fwd', C.byref(d), sp)
+            raw = self._buf('raw_%dx%dx%d' % (H, W, rc.N_out), (B, H, W, rc.N_out), torch.float32)
+            st = self._buf('stats_%d' % rc.N_pad, (B, 2, rc.N_pad), torch.float32)
+            L.call('b200sp_conv_kwsum', T.data_ptr(), raw.data_ptr(), st.data_ptr(), B, H, W, Wd, rc.Nt, rc.k, rc.Co, rc.N_out, rc.N_pad, sp)
+            cv = self.convs['c10']
+        else:
+            raw, st, cv = self._conv('c10', pl, B, Hd, Wd, H, W)
         sc, sh = self._finalize(st, cv, B, H * W, gb, ('layers.10', ''))
         if out is None:
             out = torch.empty(B, 3, H, W, dtype=torch.float32, device=self.device)
