@@ -61,6 +61,7 @@ struct TcgArgs {
     uint32_t off_raw, off_stg, off_stat, off_bar;   // dynamic smem carve-up (from the 1024-aligned base)
     uint32_t tmem_cols;
     int nacc;                        // TMEM accumulator ring depth (2 or 4)
+    int acc_cols;                    // TMEM columns per ring slot: BN, or 2*BN when the 3xTF32 correction terms have their own accumulator
     int split_epi;                   // one column chunk per tile: the two epilogue warp sets take alternate tiles
     void* out;
     const float* bias;
@@ -489,7 +490,11 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
             const Item w = get_item(g, it);
             mbar_wait_guard(&tempty[acc], tpar, g.wait_mode);
             tc::tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * g.BN;
+            const uint32_t d_tmem = tmem_base + acc * g.acc_cols;
+            // 3xTF32: the two correction products (lo*hi, hi*lo) go to a SECOND accumulator and are added in fp32-RN by the
+            // epilogue.  tcgen05 accumulates with round-toward-zero, so every MMA into the large accumulator costs up to one
+            // ulp of bias; keeping the small terms out of it cuts the number of such truncations from 3K/8 to K/8.
+            const uint32_t d_corr = d_tmem + (g.acc_cols > g.BN ? g.BN : 0);
             for (int kb = w.kb0; kb < w.kb1; ++kb) {
                 if (lane == 0) TL(4, tlm);
                 mbar_wait_guard(&full[os], fpar, g.wait_mode);
@@ -508,9 +513,10 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
                         if (ks < nks) {
                             const uint32_t accum = ks > 0 ? 1u : first;
                             if (E::TF32) {
-                                tc::umma<true>(d_tmem, mk(al + ks * A_STEP, A_HIW), mk(bh + ks * B_STEP, B_HIW), idesc, accum);
-                                tc::umma<true>(d_tmem, mk(ah + ks * A_STEP, A_HIW), mk(bl + ks * B_STEP, B_HIW), idesc, 1u);
-                                tc::umma<true>(d_tmem, mk(ah + ks * A_STEP, A_HIW), mk(bh + ks * B_STEP, B_HIW), idesc, 1u);
+                                const bool split = g.acc_cols > g.BN;
+                                tc::umma<true>(d_corr, mk(al + ks * A_STEP, A_HIW), mk(bh + ks * B_STEP, B_HIW), idesc, accum);
+                                tc::umma<true>(d_corr, mk(ah + ks * A_STEP, A_HIW), mk(bl + ks * B_STEP, B_HIW), idesc, 1u);
+                                tc::umma<true>(d_tmem, mk(ah + ks * A_STEP, A_HIW), mk(bh + ks * B_STEP, B_HIW), idesc, split ? accum : 1u);
                             } else {
                                 tc::umma<false>(d_tmem, mk(ah + ks * A_STEP, A_HIW), mk(bh + ks * B_STEP, B_HIW), idesc, accum);
                             }
@@ -574,7 +580,8 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
             cur_q0 = w.q0;
             mbar_wait_sleep(&tfull[acc], tpar);
             tc::tc_fence_after();
-            const uint32_t t_row = tmem_base + acc * g.BN + ((uint32_t)(lq * 32) << 16);
+            const uint32_t t_row = tmem_base + acc * g.acc_cols + ((uint32_t)(lq * 32) << 16);
+            const bool split_acc = g.acc_cols > g.BN;
             if (last_chunk < 0) {                        // nothing to read for this warp: release immediately
                 tc::tc_fence_before();
                 __syncwarp();
@@ -593,6 +600,18 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
                     for (int i = 0; i < 16; ++i) { r[i] = r16[i]; r[16 + i] = 0u; }
                 }
                 tc::tmem_ld_wait();
+                if (split_acc) {                // add the correction accumulator (fp32 round-to-nearest), 16 columns at a time
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        if (hh * 16 < ncol) {
+                            uint32_t q16[16];
+                            tc::tmem_ld16(t_row + g.BN + c0 + hh * 16, q16);
+                            tc::tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) r[hh * 16 + i] = __float_as_uint(__uint_as_float(r[hh * 16 + i]) + __uint_as_float(q16[i]));
+                        }
+                    }
+                }
                 if (ci == last_chunk) {         // accumulator drained by this warp: hand TMEM back to the MMA warp
                     tc::tc_fence_before();
                     __syncwarp();
@@ -793,10 +812,15 @@ int launch_cfg(TcgArgs& a, cudaStream_t st) {
     a.kb_per_split = ceil_div(a.nkb, a.splits);
     a.splits = ceil_div(a.nkb, a.kb_per_split);
     const uint32_t smem = a.off_bar + 256 + 1024;
-    a.nacc = 4 * BN <= 512 ? 4 : 2;
+    {
+        static int split_env = -1;
+        if (split_env < 0) { const char* e = getenv("B200SP_TCG_SPLIT_ACC"); split_env = e ? atoi(e) : 1; }
+        a.acc_cols = (E::TF32 && split_env && 2 * 2 * BN <= 512) ? 2 * BN : BN;
+    }
+    a.nacc = 4 * a.acc_cols <= 512 ? 4 : 2;
     a.split_epi = (BN <= 32 && numQt == 1 && EPI_SETS == 2) ? 1 : 0;
     uint32_t cols = 32;
-    while (cols < (uint32_t)(a.nacc * BN)) cols <<= 1;
+    while (cols < (uint32_t)(a.nacc * a.acc_cols)) cols <<= 1;
     a.tmem_cols = cols;
     const int total = numPt * numQt * a.splits;
     const int grid = total < NUM_SMS ? total : NUM_SMS;
