@@ -59,3 +59,12 @@ def test_train_cli_with_style_augmentation_flag(tmp_path):
     assert (r.returncode == 0) == have, r.stderr[-2000:]
     if not have:
         assert 'checkpoints not found' in r.stderr
+
+
+def test_train_cli_spn(tmp_path):
+    _run('train.py', ['--model_name', 'spn', '--optimizer', 'adamw', '--batch_size', '4', '--synthetic_data', '2', '--max_epochs', '1',
+                      '--input_shape', '227', '227', '--savedir', 'ck', '--logdir', 'lg', '--start_over'], str(tmp_path))
+    ck = torch.load(str(tmp_path / 'ck' / 'checkpoint.pth.tar'), map_location='cpu', weights_only=False)
+    assert ck['model'] == 'spn' and ck['state_dict']['fc6.weight'].shape == (4096, 9216)
+    assert ck['state_dict']['conv1.weight'].shape == (96, 3, 11, 11)
+    assert all(torch.isfinite(v).all() for v in ck['state_dict'].values())
