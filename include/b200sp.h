@@ -190,6 +190,10 @@ typedef struct b200sp_convtc_desc {
     float *stats;
     int32_t C, B, Hq, Wq, Ho, Wo, N_pad, N_out, n_chunks, pad_;
     b200sp_convtc_chunk chunks[B200SP_CONVTC_MAX_CHUNKS];
+    /* output scatter (all zero => dense [B][Ho][Wo]): valid grid position (ph, pw) of image b is stored at pixel
+     * (ph*sy + oy, pw*sx + ox) of an [B][OH][OW][N_out] tensor -- the four phase convolutions of a sub-pixel
+     * (upsample x2 + 3x3) layer interleave their outputs this way */
+    int32_t OH, OW, sy, sx, oy, ox;
 } b200sp_convtc_desc;
 int b200sp_convtc_fwd(const b200sp_convtc_desc *d, void *stream);
 
@@ -207,7 +211,9 @@ int b200sp_in_finalize(float *stats, const float *gamma, const float *beta, int 
                        int B, int C, int N_pad, int HW, float eps, void *stream);
 /* v = act(raw*scale + shift) (+ res_in), written (a) as the NEXT conv's bf16 input plane(s): reflection padding
  * `pad`, nearest upsampling `up` (1|2), stride-2 phase split `ps` (1|2 -> 1|4 planes of [B][Hd][Wd][Cd]);
- * (b) optionally as the fp32 residual stream res_out [B][Hs][Ws][C] (interior pixels, ps == up == 1 only). */
+ * (b) optionally as the fp32 residual stream res_out [B][Hs][Ws][C] (interior pixels, ps == up == 1 only).
+ * pad_mode 0: reflection (ReflectionPad2d); 1: edge replication (what reflection of a x2-nearest-upsampled image is in
+ * source coordinates: used by the sub-pixel form of the upsampling convolutions). */
 typedef struct b200sp_in_apply_desc {
     const float *raw;        /* [B][Hs][Ws][Cs] */
     const float *scale, *shift;   /* [B][C] */
@@ -215,6 +221,7 @@ typedef struct b200sp_in_apply_desc {
     float *res_out;          /* or NULL */
     void *planes[4];
     int32_t B, Hs, Ws, Cs, C, act, pad, up, ps, Hd, Wd, Cd;
+    int32_t pad_mode, pad2_;
 } b200sp_in_apply_desc;
 int b200sp_in_apply(const b200sp_in_apply_desc *d, void *stream);
 /* last layer (ghiasi.py:135): out_nchw[b,c,h,w] = sigmoid(raw[b,h,w,c]*scale[b,c] + shift[b,c]), c < C */

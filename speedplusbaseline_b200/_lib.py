@@ -49,13 +49,15 @@ class ConvDesc(C.Structure):
     _fields_ = [('planes', vp * 4), ('w', vp), ('out', vp), ('stats', vp),
                 ('C', C.c_int32), ('B', C.c_int32), ('Hq', C.c_int32), ('Wq', C.c_int32), ('Ho', C.c_int32), ('Wo', C.c_int32),
                 ('N_pad', C.c_int32), ('N_out', C.c_int32), ('n_chunks', C.c_int32), ('pad_', C.c_int32),
-                ('chunks', ConvChunk * CONVTC_MAX_CHUNKS)]
+                ('chunks', ConvChunk * CONVTC_MAX_CHUNKS),
+                ('OH', C.c_int32), ('OW', C.c_int32), ('sy', C.c_int32), ('sx', C.c_int32), ('oy', C.c_int32), ('ox', C.c_int32)]
 
 
 class InApplyDesc(C.Structure):
     _fields_ = [('raw', vp), ('scale', vp), ('shift', vp), ('res_in', vp), ('res_out', vp), ('planes', vp * 4),
                 ('B', C.c_int32), ('Hs', C.c_int32), ('Ws', C.c_int32), ('Cs', C.c_int32), ('C', C.c_int32), ('act', C.c_int32),
-                ('pad', C.c_int32), ('up', C.c_int32), ('ps', C.c_int32), ('Hd', C.c_int32), ('Wd', C.c_int32), ('Cd', C.c_int32)]
+                ('pad', C.c_int32), ('up', C.c_int32), ('ps', C.c_int32), ('Hd', C.c_int32), ('Wd', C.c_int32), ('Cd', C.c_int32),
+                ('pad_mode', C.c_int32), ('pad2_', C.c_int32)]
 
 
 def _load():

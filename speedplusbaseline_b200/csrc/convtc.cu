@@ -38,6 +38,7 @@ struct alignas(64) ConvArgs {
     int32_t chunk_shift[B200SP_CONVTC_MAX_CHUNKS];
     int32_t n_chunks, n_stages, BN, N_out;
     int32_t R, plane_sz, Wq, Ho, Wo, num_tiles;
+    int32_t OH, OW, sy, sx, oy, ox;
     uint32_t stage_bytes, off_bar, off_stat, tmem_cols;
     float* out;
     float* stats;
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(CT_NT, 1) convtc_kernel(const __grid_constant_
             const int b_lo = m0 / g.plane_sz;
             const int m_last = min(m0 + CT_BM - 1, g.R - 1);
             const bool two = (m_last / g.plane_sz) != b_lo;
-            float* orow = g.out + ((size_t)(b * g.Ho + ph) * g.Wo + pw) * g.N_out;
+            float* orow = g.out + ((size_t)(b * g.OH + ph * g.sy + g.oy) * g.OW + pw * g.sx + g.ox) * g.N_out;
             ct_wait_sleep(&tfull[acc], (ni >> 1) & 1);
             tc::tc_fence_after();
             const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
@@ -271,6 +272,11 @@ extern "C" int b200sp_convtc_fwd(const b200sp_convtc_desc* d, void* stream) {
     }
     a.n_chunks = d->n_chunks; a.BN = BN; a.N_out = d->N_out;
     a.R = (int)R; a.plane_sz = d->Hq * d->Wq; a.Wq = d->Wq; a.Ho = d->Ho; a.Wo = d->Wo;
+    if (d->sy == 0 && d->sx == 0) { a.OH = d->Ho; a.OW = d->Wo; a.sy = a.sx = 1; a.oy = a.ox = 0; }
+    else {
+        a.OH = d->OH; a.OW = d->OW; a.sy = d->sy; a.sx = d->sx; a.oy = d->oy; a.ox = d->ox;
+        if (a.sy < 1 || a.sx < 1 || a.oy < 0 || a.ox < 0 || (d->Ho - 1) * a.sy + a.oy >= a.OH || (d->Wo - 1) * a.sx + a.ox >= a.OW) return B200SP_EINVAL;
+    }
     a.num_tiles = (int)((R + CT_BM - 1) / CT_BM);
     a.stage_bytes = CT_A_BYTES + BN * 128;
     const uint32_t fixed = 4 * BN * 4 + 512;

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(SA_NT) in_apply_kernel(const b200sp_in_apply_d
         const int b = (int)(r / d.Hd);
         const int qy = q / d.ps, qx = q - qy * d.ps;
         const int Y = y * d.ps + qy - d.pad, X = x * d.ps + qx - d.pad;
-        const int uy = reflect(Y, Hup), ux = reflect(X, Wup);
+        const int uy = d.pad_mode ? min(max(Y, 0), Hup - 1) : reflect(Y, Hup), ux = d.pad_mode ? min(max(X, 0), Wup - 1) : reflect(X, Wup);
         const int sy = d.up == 2 ? uy >> 1 : uy, sx = d.up == 2 ? ux >> 1 : ux;
         const int c0 = cg * 8;
         float v[8];
