@@ -685,8 +685,9 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
                             }
                             Vec4<T>::st(outT + off, v);
                         } else {
-                            atomicAdd(outF + off, v.x); atomicAdd(outF + off + 1, v.y);
-                            atomicAdd(outF + off + 2, v.z); atomicAdd(outF + off + 3, v.w);
+                            // one 16-byte vector reduction instead of four scalar atomics (sm_90+: red.global.add.v4.f32)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(outF + off), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                                         : "memory");
                         }
                     }
                 }
