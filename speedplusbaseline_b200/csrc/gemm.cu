@@ -234,9 +234,8 @@ __global__ void __launch_bounds__(NT, 2) gemm_kernel(const GemmArgs g) {
                         }
                     } else {
                         if (ok) {
-                            float* o = reinterpret_cast<float*>(g.out) + off;
-                            atomicAdd(o, v0);
-                            atomicAdd(o + 1, v1);
+                            float* o = reinterpret_cast<float*>(g.out) + off;      // even column, Q even: 8-byte aligned
+                            asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(o), "f"(v0), "f"(v1) : "memory");
                         }
                     }
                 }
