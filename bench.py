@@ -300,6 +300,14 @@ def main():
                 'share_of_step': dom['share'], 'us_per_launch': dom['us'], 'algorithmic_bytes_per_launch': dom['bytes'],
                 'step_roofline_frac': prof['step_roofline_ms'] / (ms / K),
                 'step_algorithmic_gb': prof['step_bytes'] / 1e9}
+        # the metric's second half, "conv tensor-pipe % of peak" (SURVEY.md §8 d-1): dense conv/FC FLOPs of the reference
+        # graph (2.3345 GFLOP per image for a train step; depthwise excluded, it is CUDA-core work) / step time / measured
+        # dense bf16 peak.  The fp32 path issues 3 tf32 MMAs per product (tf32 rate = bf16/2), so its own ceiling is peak/6.
+        dense_gf = 2.3345 * BATCH
+        tflops = dense_gf / (ms / K)            # GFLOP / ms == TFLOP/s per GPU
+        roof['tensor_pipe'] = {'dense_gflop_per_step': dense_gf, 'achieved': tflops, 'peak': tf, 'unit': 'TFLOP/s',
+                               'frac': tflops / tf, 'peak_source': which + ' (cuBLAS bf16 sustained)',
+                               'mma_per_product': 3 if args.dtype == 'fp32' else 1}
         if args.profile_out:
             with open(args.profile_out, 'w') as f:
                 f.write(prof['table'])
