@@ -298,6 +298,13 @@ typedef struct b200sp_adamw_hp {   /* lives in DEVICE memory so CUDA graphs can 
 int b200sp_grad_sqnorm(const float *g, int64_t n, b200sp_adamw_hp *hp, void *stream);
 int b200sp_adamw_step(float *p, const float *g, float *m, float *v, void *p_lowp /*bf16 copy or NULL*/,
                       int64_t n, b200sp_adamw_hp *hp, void *stream);
+/* The other --optimizer choices (build.py:63-71: torch.optim.SGD(momentum) / RMSprop(alpha=cfg.momentum) /
+ * Adam(betas=(cfg.momentum, .999)), all with coupled L2 weight decay), as ONE launch over the flat buffer after the same
+ * clip.  hp->beta1 carries momentum (SGD) / alpha (RMSprop) / beta1 (Adam); s1 = momentum_buffer / square_avg / exp_avg,
+ * s2 = exp_avg_sq (Adam only, else NULL).  kind == B200SP_OPT_ADAMW forwards to b200sp_adamw_step. */
+enum { B200SP_OPT_ADAMW = 0, B200SP_OPT_SGD = 1, B200SP_OPT_RMSPROP = 2, B200SP_OPT_ADAM = 3 };
+int b200sp_optim_step(int kind, float *p, const float *g, float *s1, float *s2, void *p_lowp /*bf16 copy or NULL*/,
+                      int64_t n, b200sp_adamw_hp *hp, void *stream);
 
 #ifdef __cplusplus
 }

@@ -10,6 +10,7 @@ from . import _build
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_RELU6, ACT_LEAKY02, ACT_SIGMOID = 0, 1, 2, 3, 4
 VT_PLAIN, VT_BNACT, VT_DY = 0, 1, 2
+OPT_ADAMW, OPT_SGD, OPT_RMSPROP, OPT_ADAM = 0, 1, 2, 3
 BF16_ENABLED = os.environ.get('B200SP_ENABLE_BF16', '0') == '1'   # experimental bf16 storage for --use_fp16
 
 vp = C.c_void_p
@@ -126,6 +127,7 @@ _SIGS = {
     'b200sp_scale_dev': ([vp, i64, vp, f32, i32, vp], i32),
     'b200sp_grad_sqnorm': ([vp, i64, vp, vp], i32),
     'b200sp_adamw_step': ([vp, vp, vp, vp, vp, i64, vp, vp], i32),
+    'b200sp_optim_step': ([i32, vp, vp, vp, vp, vp, i64, vp, vp], i32),
 }
 for _n, (_a, _r) in _SIGS.items():
     _f = getattr(lib, _n)

@@ -3,16 +3,16 @@
 get_model dispatches on cfg.model_name / cfg.dann exactly like the reference; get_optimizer returns the
 fused flat-buffer AdamW for `--optimizer adamw` (the north-star path; clip mode follows the loop that
 will drive it: global-norm 1.0 for KRN/DANN, trainer.py:97 / dann.py:99, value 1.0 for SPN,
-trainer.py:184).  sgd / rmsprop / adam are outside the hot path: they fall back to
-the stock torch optimizers on the module's aliased Parameters, which works because `.grad` aliases the
-flat gradient buffer.
+trainer.py:184).  sgd / rmsprop / adam map to the same flat-buffer design
+(optim.FusedSGD / FusedRMSprop / FusedAdam -> b200sp_optim_step) with the reference's argument mapping
+(`cfg.momentum` is SGD's momentum, RMSprop's alpha and Adam's beta1, build.py:63-71).
 """
 import logging
 
 import torch
 
 from .. import _lib as L
-from ..optim import FusedAdamW
+from ..optim import FusedAdam, FusedAdamW, FusedRMSprop, FusedSGD
 from .park2019 import KeypointRegressionNet
 from .revgrad import RevGrad
 
@@ -46,14 +46,15 @@ def get_model(cfg):
 
 def get_optimizer(cfg, model):
     param = filter(lambda p: p.requires_grad, model.parameters())
+    clip_mode = 2 if cfg.model_name == 'spn' and not cfg.dann else 1
+    clip = dict(clip_mode=clip_mode, max_norm=1.0, clip_value=1.0)
     if cfg.optimizer == 'sgd':
-        optimizer = torch.optim.SGD(param, lr=cfg.lr, momentum=cfg.momentum, weight_decay=cfg.weight_decay)
+        optimizer = FusedSGD(model._store, param, lr=cfg.lr, momentum=cfg.momentum, weight_decay=cfg.weight_decay, **clip)
     elif cfg.optimizer == 'rmsprop':
-        optimizer = torch.optim.RMSprop(param, lr=cfg.lr, alpha=cfg.momentum, weight_decay=cfg.weight_decay)
+        optimizer = FusedRMSprop(model._store, param, lr=cfg.lr, alpha=cfg.momentum, weight_decay=cfg.weight_decay, **clip)
     elif cfg.optimizer == 'adam':
-        optimizer = torch.optim.Adam(param, lr=cfg.lr, betas=(cfg.momentum, 0.999), weight_decay=cfg.weight_decay)
+        optimizer = FusedAdam(model._store, param, lr=cfg.lr, betas=(cfg.momentum, 0.999), weight_decay=cfg.weight_decay, **clip)
     elif cfg.optimizer == 'adamw':
-        clip_mode = 2 if cfg.model_name == 'spn' and not cfg.dann else 1
         optimizer = FusedAdamW(model._store, param, lr=cfg.lr, betas=(cfg.momentum, 0.999),
                                weight_decay=cfg.weight_decay, clip_mode=clip_mode, max_norm=1.0, clip_value=1.0)
     else:
