@@ -286,6 +286,16 @@ int b200sp_dann_head_bwd(void *h_inout, const float *dz, const float *pooled, co
 /* x *= s[0]*mul with s in DEVICE memory: the gradient-reversal factor -lambda (revgrad.py:52-56) */
 int b200sp_scale_dev(void *x, int64_t n, const float *s, float mul, int dtype, void *stream);
 
+/* ---- evaluation tail on the device (src/core/inference.py) ----
+ * b200sp_topk_softmax: inference.py:180-181 `topW, topC = torch.topk(weights, num_neighbors, dim=1); topW = softmax(topW, 1)`.
+ *   logits [B,N] fp32 -> top_w [B,k] (softmax over the k winners, descending), top_idx [B,k] int64 (ties: lowest index),
+ *   top_raw [B,k] (optional, may be NULL: the un-normalised winners).  1 <= k <= 32, k <= N, N*4 <= 200 KB.
+ * b200sp_kpt_denorm: inference.py:236-243 `corners2D[:,0] = x*(xmax-xmin)+xmin; [:,1] = y*(ymax-ymin)+ymin` with numpy's
+ *   fp32 rounding (no FMA).  logits [B,2K] interleaved (x0,y0,x1,y1,..: park2019.py:163-164), bbox [B,4] =
+ *   (xmin,xmax,ymin,ymax) in pixels -> out [B,K,2] pixels. */
+int b200sp_topk_softmax(const float *logits, float *top_w, float *top_raw, int64_t *top_idx, int B, int N, int k, void *stream);
+int b200sp_kpt_denorm(const float *logits, const float *bbox, float *out, int B, int K, void *stream);
+
 /* ---- optimizer (build.py:72-74 torch.optim.AdamW; trainer.py:97 clip_grad_norm_) ---- */
 typedef struct b200sp_adamw_hp {   /* lives in DEVICE memory so CUDA graphs can replay */
     float lr, beta1, beta2, eps, weight_decay, max_norm, clip_value, grad_scale;

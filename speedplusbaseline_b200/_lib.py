@@ -128,6 +128,8 @@ _SIGS = {
     'b200sp_grad_sqnorm': ([vp, i64, vp, vp], i32),
     'b200sp_adamw_step': ([vp, vp, vp, vp, vp, i64, vp, vp], i32),
     'b200sp_optim_step': ([i32, vp, vp, vp, vp, vp, i64, vp, vp], i32),
+    'b200sp_topk_softmax': ([vp, vp, vp, vp, i32, i32, i32, vp], i32),
+    'b200sp_kpt_denorm': ([vp, vp, vp, i32, i32, vp], i32),
 }
 for _n, (_a, _r) in _SIGS.items():
     _f = getattr(lib, _n)

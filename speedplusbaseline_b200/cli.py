@@ -81,14 +81,18 @@ def resume(cfg, model, optimizer, device):
 
 
 def validate(cfg, model, test_loader, epoch, writer, device):
-    """The reference's evaluation loop (src/core/inference.py:43-249: batch-1 forward, EPnP, SPEED
-    metrics) driving our module -- the module keeps the eval-mode contract `(xc.cpu(), yc.cpu())`."""
+    """Evaluation (src/core/inference.py:43-221).  On the GPU: batched forward + on-device post-processing tail
+    (core/inference.py); with --no_cuda: the reference's own loop.  EPnP / SPEED metrics are the
+    reference's CPU code either way (out of scope)."""
     reference_modules(cfg)
     from scipy.io import loadmat
-    from src.core import inference
     from src.utils.utils import load_tango_3d_keypoints, load_camera_intrinsics
     corners3D = load_tango_3d_keypoints(os.path.join(cfg.reference_root, cfg.keypts_3d_model))
     cameraMatrix, distCoeffs = load_camera_intrinsics(os.path.join(cfg.dataroot, cfg.dataname, 'camera.json'))
     att = loadmat(os.path.join(cfg.reference_root, cfg.attitude_class))['qClass']
+    if device.type == 'cuda':
+        from .core import inference
+    else:
+        from src.core import inference
     fn = getattr(inference, 'valid_' + cfg.model_name)
     return fn(epoch, cfg, model, test_loader, cameraMatrix, distCoeffs, corners3D, writer, device, att)

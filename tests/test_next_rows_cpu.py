@@ -39,3 +39,25 @@ def test_oracle_optimizers_match_reference_factory(golden_dir, name):
     # the trajectories are not trivially equal to the start (every step moved the parameters)
     p0 = torch.cat([p.reshape(-1) for p in synth_problem()[0]]).numpy()
     assert np.abs(g[0] - p0).max() > 1e-4 and np.abs(g[-1] - g[0]).max() > 1e-4
+
+
+# ---- row f2: evaluation tail ----------------------------------------------------------------------
+def _tie_free_rows(w, k):
+    """rows whose k+1 largest values are pairwise distinct (torch.topk's order among exact ties is unspecified)."""
+    s = -np.sort(-w, axis=1)[:, :k + 1]
+    return np.array([len(np.unique(r)) == k + 1 for r in s])
+
+
+def test_oracle_postproc_matches_reference_loops(golden_dir):
+    from oracle import postproc
+    from oracle.make_golden_postproc import K_NB, synth_inputs
+    g = np.load(os.path.join(golden_dir, 'postproc.npz'))
+    w, x, y, bb = (t.numpy() for t in synth_inputs())
+    tw, ti = postproc.spn_top_classes(w, K_NB)
+    free = _tie_free_rows(w, K_NB)
+    assert free.sum() >= 4 and not free.all()              # the fixture holds both kinds of rows
+    assert (ti[free] == g['top_idx'][free]).all()          # bit-exact indices where the order is defined
+    # every row, ties included: the selected VALUES are the reference's, in the same (descending) order
+    assert (np.take_along_axis(w, ti, 1) == np.take_along_axis(w, g['top_idx'], 1)).all()
+    np.testing.assert_allclose(tw, g['top_w'], rtol=1e-6, atol=1e-9)
+    assert (postproc.krn_keypoints_pix(x, y, bb) == g['kpt_pix']).all()       # fp32, bit-exact
