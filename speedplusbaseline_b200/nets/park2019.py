@@ -104,6 +104,27 @@ class KeypointRegressionNet(EngineModule):
         self.engine = KRNEngine(num_keypoints, prefix=_prefix, dann=_dann, device=device, dtype=dtype)
         self._register_store(self.engine.store, self.engine.key_order)
         default_init(self.engine.store, seed)
+        if seed is None:
+            self.load_imagenet_backbone()
+
+    def load_imagenet_backbone(self, checkpoint=None):
+        """park2019.py:107 `models.mobilenet_v2(pretrained=True)`: the ImageNet backbone.  There is no network here, so the
+        weights are taken from where torchvision would have cached its download
+        ($TORCH_HOME/hub/checkpoints/mobilenet_v2-b0353104.pth) or from an explicit path / state dict; when neither exists
+        the backbone keeps its random initialisation (warned).  Seeded constructions (tests, bench) never load."""
+        import logging
+        import os
+        from ..importers import load_mobilenetv2_backbone
+        if checkpoint is None:
+            hub = os.path.join(os.environ.get('TORCH_HOME', os.path.join(os.path.expanduser('~'), '.cache', 'torch')), 'hub', 'checkpoints')
+            for fn in ('mobilenet_v2-b0353104.pth', 'mobilenet_v2-7ebf99e0.pth'):
+                if os.path.exists(os.path.join(hub, fn)):
+                    checkpoint = os.path.join(hub, fn)
+                    break
+        if checkpoint is None:
+            logging.getLogger(__name__).warning('   - no cached torchvision MobileNetV2 checkpoint: backbone keeps its random initialisation')
+            return []
+        return load_mobilenetv2_backbone(self, checkpoint)
 
     def forward(self, x, y=None):
         eng = self.engine

@@ -36,6 +36,9 @@ class RevGrad(EngineModule):
         self.engine = KRNEngine(num_keypoints, prefix='net.', dann=True, device=device, dtype=dtype)
         self._register_store(self.engine.store, self.engine.key_order)
         default_init(self.engine.store, seed)
+        if seed is None:
+            from .park2019 import KeypointRegressionNet
+            KeypointRegressionNet.load_imagenet_backbone(self)       # revgrad.py:64 builds the same pretrained KRN
         self._slot = 0
 
     def begin_step(self):

@@ -54,17 +54,8 @@ class SpacecraftPoseNet(EngineModule):
         if not os.path.exists(weight_path):
             logger.warning('   - %s not found: SPN convolutions keep their random initialisation', weight_path)
             return
-        weights_dict = np.load(weight_path, allow_pickle=True, encoding='bytes').item()
-        sd = {}
-        for name in weights_dict:
-            key = name.decode() if isinstance(name, bytes) else name
-            if key in ('conv1', 'conv2', 'conv3', 'conv4', 'conv5'):
-                for data in weights_dict[name]:
-                    if len(data.shape) == 4:
-                        sd[key + '.weight'] = torch.from_numpy(np.transpose(data, (3, 2, 0, 1))).float()
-                    else:
-                        sd[key + '.bias'] = torch.from_numpy(data).float()
-        self._store.load_state_dict(sd, strict=False)
+        from ..importers import load_alexnet_npy
+        load_alexnet_npy(self, weight_path)
 
     def forward(self, x):
         eng = self.engine

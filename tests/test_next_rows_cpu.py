@@ -61,3 +61,96 @@ def test_oracle_postproc_matches_reference_loops(golden_dir):
     assert (np.take_along_axis(w, ti, 1) == np.take_along_axis(w, g['top_idx'], 1)).all()
     np.testing.assert_allclose(tw, g['top_w'], rtol=1e-6, atol=1e-9)
     assert (postproc.krn_keypoints_pix(x, y, bb) == g['kpt_pix']).all()       # fp32, bit-exact
+
+
+# ---- row f3: pretrained-weight importers ------------------------------------------------------------
+def _tv_mobilenet_sd(seed=3):
+    import torchvision
+    torch.manual_seed(seed)
+    m = torchvision.models.mobilenet_v2(weights=None)
+    for mod in m.modules():                       # non-trivial BN statistics, like a trained checkpoint
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.1)
+            mod.running_var.uniform_(0.5, 1.5)
+            mod.weight.data.uniform_(0.5, 1.5)
+            mod.bias.data.normal_(0, 0.1)
+            mod.num_batches_tracked.fill_(7)
+    return m.state_dict()
+
+
+@pytest.mark.parametrize('dann', [False, True])
+def test_mobilenetv2_importer_fills_every_backbone_key(dann):
+    from speedplusbaseline_b200 import importers
+    from speedplusbaseline_b200.krn_engine import krn_layout
+    from speedplusbaseline_b200.params import ParamStore
+    prefix = 'net.' if dann else ''
+    W, BN, order = krn_layout(11, prefix=prefix, dann=dann)
+    st = ParamStore(W, BN, torch.device('cpu'))
+    before = st.state_dict(order)
+    tv = _tv_mobilenet_sd()
+    written = importers.load_mobilenetv2_backbone(st, tv)
+    after = st.state_dict(order)
+    base_keys = [k for k in order if k.startswith(prefix + 'base.')]
+    assert sorted(written) == sorted(base_keys)                         # every backbone key, nothing else
+    for k in order:
+        if k in written:
+            src = tv['features.' + k[len(prefix) + len('base.'):]]
+            assert torch.equal(after[k], src.to(after[k].dtype)), k    # values survive the native-layout round trip
+        else:
+            assert torch.equal(after[k], before[k]), k                 # extras / head / domain classifier untouched
+    assert not any(k.startswith(prefix + 'base.18') for k in written)
+    with pytest.raises(KeyError):
+        importers.mobilenetv2_to_krn({k: v for k, v in tv.items() if not k.startswith('features.7.')})
+
+
+def test_alexnet_npy_importer_matches_reference_transposition(tmp_path):
+    from speedplusbaseline_b200 import importers
+    from speedplusbaseline_b200.params import ParamStore
+    from speedplusbaseline_b200.spn_engine import CONVS, spn_layout
+    rng = np.random.default_rng(5)
+    dump = {}
+    for name, ci, co, k, s, p, g in CONVS:       # Caffe layout [H, W, Cin/groups, Cout] + bias, bytes keys like the real file
+        dump[name.encode()] = [rng.standard_normal((k, k, ci // g, co)).astype(np.float32), rng.standard_normal(co).astype(np.float32)]
+    dump[b'fc6'] = [rng.standard_normal((9216, 16)).astype(np.float32), rng.standard_normal(16).astype(np.float32)]   # ignored
+    path = os.path.join(str(tmp_path), 'bvlc_alexnet.npy')
+    np.save(path, dump, allow_pickle=True)
+    W, order = spn_layout(40)
+    st = ParamStore(W, [], torch.device('cpu'))
+    written = importers.load_alexnet_npy(st, path)
+    assert sorted(written) == sorted(n + s for n, *_ in CONVS for s in ('.weight', '.bias'))
+    sd = st.state_dict(order)
+    for name, *_ in CONVS:
+        w, b = dump[name.encode()]
+        # spn.py:118-121: np.transpose(data, (3, 2, 0, 1)) -> conv.weight
+        assert torch.equal(sd[name + '.weight'], torch.from_numpy(np.transpose(w, (3, 2, 0, 1)).copy()))
+        assert torch.equal(sd[name + '.bias'], torch.from_numpy(b))
+    assert float(sd['fc6.weight'].abs().sum()) == 0.0                    # FC layers are not part of the dump the reference reads
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/src'), reason='needs the reference checkout (build container only)')
+def test_mobilenetv2_importer_agrees_with_reference_module():
+    """the reference builds `base` from torchvision's features[:-1] (park2019.py:107-108): with the same RNG stream its
+    state_dict must equal the importer's mapping of the torchvision checkpoint, key for key."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, types
+sys.argv = ['x']; sys.path.insert(0, '/root/reference'); sys.path.insert(0, %r)
+for n in ('matplotlib', 'matplotlib.pyplot', 'matplotlib.patches'):
+    sys.modules[n] = types.ModuleType(n)
+sys.modules['matplotlib'].use = lambda *a, **k: None
+import torch, torchvision.models as tvm
+_mb = tvm.mobilenet_v2
+tvm.mobilenet_v2 = lambda pretrained=False, **kw: _mb(weights=None, **kw)
+from src.nets.park2019 import KeypointRegressionNet
+from speedplusbaseline_b200 import importers
+torch.manual_seed(11); ref = KeypointRegressionNet(11).state_dict()
+torch.manual_seed(11); tv = _mb(weights=None).state_dict()
+mapped = importers.mobilenetv2_to_krn(tv)
+assert sorted(mapped) == sorted(k for k in ref if k.startswith('base.')), 'key sets differ'
+assert all(torch.equal(mapped[k], ref[k]) for k in mapped)
+print('OK', len(mapped))
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, B200SP_NO_AUTOBUILD='1'))
+    assert r.returncode == 0 and 'OK 306' in r.stdout, r.stdout + r.stderr
