@@ -183,6 +183,25 @@ def secondary_workloads(dev, stepper, d_img, d_tgt, k=8):
     yc[:, :5] = 0.2
     ms = _time_steps(lambda: ss.step(x, yc, yc), 2, k)
     out['spn_train_bs32_dropout0.5'] = {'ms': ms, 'images_per_sec': 32 / ms * 1e3}
+    del spn, opt, ss, x, yc
+    torch.cuda.empty_cache()
+    # the reference's per-sample transform stack as one batched device call -- 48 SPEED+-sized grey
+    # frames (1200x1920 uint8, resident in HBM) -> crop + Pillow-exact bilinear resize + ToTensor + rotate/flip +
+    # brightness/contrast + noise -> [48,3,224,224] fp32.  Host-side decision sampling and struct upload are inside the timing.
+    try:
+        import numpy as np
+        from speedplusbaseline_b200.datasets.transforms import build_transforms
+        tf = build_transforms('krn', (HW, HW), p_aug=0.5, is_train=True, device=dev, generator=torch.Generator().manual_seed(1))
+        frames = torch.randint(0, 256, (BATCH, 1200, 1920), dtype=torch.uint8, device=dev)
+        rng = np.random.default_rng(1)
+        cx, cy, sz = rng.uniform(500, 1400, BATCH), rng.uniform(400, 800, BATCH), rng.uniform(150, 700, BATCH)
+        bbox = np.stack([cx - sz / 2, cx + sz / 2, cy - sz / 2, cy + sz / 2], 1).astype(np.float32)
+        kp = np.zeros((BATCH, 2, 11), np.float32)
+        ms = _time_steps(lambda: tf(frames, bbox, kp), 2, k)
+        out['input_pipeline_bs48_1200x1920_u8'] = {'ms': ms, 'images_per_sec': BATCH / ms * 1e3, 'status': tf.status(),
+                                                    'out_gbs': BATCH * 3 * HW * HW * 4 / ms / 1e6}
+    except Exception as e:
+        out['input_pipeline_bs48_1200x1920_u8'] = {'error': repr(e)[:200]}
     return out
 
 # ------------------------------------------------------------------------------------------------

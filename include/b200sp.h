@@ -296,6 +296,30 @@ int b200sp_scale_dev(void *x, int64_t n, const float *s, float mul, int dtype, v
 int b200sp_topk_softmax(const float *logits, float *top_w, float *top_raw, int64_t *top_idx, int B, int N, int k, void *stream);
 int b200sp_kpt_denorm(const float *logits, const float *bbox, float *out, int B, int K, void *stream);
 
+/* ---- input pipeline on the device (src/datasets/transforms.py:38-246, Park2019KRNDataset.py:86-87) ----
+ * One batch of raw 8-bit frames [B,H,W,C] (C = 1 grey, replicated to RGB like `.convert('RGB')`, or 3) already in HBM ->
+ * fp32 NCHW [B,3,oh,ow] in [0,1]: crop to (x0,x1,y0,y1), Pillow BILINEAR resize (8-bit two-pass resampler, bit-exact),
+ * ToTensor, quarter-turn rotation, flip, clamp(a*x+b), clamp(x + N(0, noise_std)).  The random DECISIONS are made by the
+ * host (datasets/transforms.py follows the reference's distributions) and arrive as one b200sp_aug per image. */
+typedef struct b200sp_aug {
+    int32_t x0, x1, y0, y1;   /* crop box in frame pixels, [x0,x1) x [y0,y1)  (RandomCrop :147-152 / ResizeCrop :181-184) */
+    int32_t rot;              /* 0..3 quarter turns counter-clockwise (Rotate :40-44: angle = 90*rot) */
+    int32_t flip;             /* 0 none, 1 horizontal, 2 vertical (Flip :61-70) */
+    int32_t bc;               /* 1: apply clamp(a*image + b, 0, 1) (BrightnessContrast :97) */
+    float a, b;
+    float noise_std;          /* > 0: clamp(image + noise_std*N(0,1), 0, 1) (GaussianNoise :110-111), device RNG keyed by seed */
+    uint32_t seed;
+    int32_t pad_;
+} b200sp_aug;
+/* aug: DEVICE array [B].  coef: int32 scratch [B*2*max(oh,ow)*(2+ks)].  tmp: uint8 scratch [B*tmp_rows*ow*C].
+ * ks >= 2*ceil(max(crop extent / output extent, 1)) + 1 taps and tmp_rows >= max crop height are the caller's sizing; a box
+ * that violates them (or is empty) sets bit 0/1 of *status (DEVICE int, may be NULL) and yields zeros / truncated taps
+ * instead of writing out of bounds.  any_odd_rot: some rot is 1 or 3 (then oh must equal ow). */
+int b200sp_input_pipeline(const uint8_t *frames, int B, int H, int W, int C, const b200sp_aug *aug, int32_t *coef, uint8_t *tmp,
+                          int tmp_rows, int ks, float *out, int oh, int ow, int any_odd_rot, int *status, void *stream);
+/* keypoints [B,2,K] in frame pixels -> the crop's [0,1] frame (normalize=1, RandomCrop :156-159) -> Rotate/Flip bookkeeping */
+int b200sp_kpt_augment(const float *kpt_pix, const b200sp_aug *aug, float *out, int B, int K, int normalize, void *stream);
+
 /* ---- optimizer (build.py:72-74 torch.optim.AdamW; trainer.py:97 clip_grad_norm_) ---- */
 typedef struct b200sp_adamw_hp {   /* lives in DEVICE memory so CUDA graphs can replay */
     float lr, beta1, beta2, eps, weight_decay, max_norm, clip_value, grad_scale;

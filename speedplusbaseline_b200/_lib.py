@@ -39,6 +39,12 @@ class AdamWHp(C.Structure):
                 ('sqnorm', C.c_double), ('last_norm', C.c_float), ('pad_', C.c_float)]
 
 
+class Aug(C.Structure):          # b200sp_aug (include/b200sp.h): per-image crop box + augmentation decisions
+    _fields_ = [('x0', C.c_int32), ('x1', C.c_int32), ('y0', C.c_int32), ('y1', C.c_int32), ('rot', C.c_int32),
+                ('flip', C.c_int32), ('bc', C.c_int32), ('a', C.c_float), ('b', C.c_float), ('noise_std', C.c_float),
+                ('seed', C.c_uint32), ('pad_', C.c_int32)]
+
+
 class ConvChunk(C.Structure):
     _fields_ = [('plane', C.c_int32), ('c0', C.c_int32), ('shift', C.c_int32), ('pad_', C.c_int32)]
 
@@ -130,6 +136,8 @@ _SIGS = {
     'b200sp_optim_step': ([i32, vp, vp, vp, vp, vp, i64, vp, vp], i32),
     'b200sp_topk_softmax': ([vp, vp, vp, vp, i32, i32, i32, vp], i32),
     'b200sp_kpt_denorm': ([vp, vp, vp, i32, i32, vp], i32),
+    'b200sp_input_pipeline': ([vp, i32, i32, i32, i32, vp, vp, vp, i32, i32, vp, i32, i32, i32, vp, vp], i32),
+    'b200sp_kpt_augment': ([vp, vp, vp, i32, i32, i32, vp], i32),
 }
 for _n, (_a, _r) in _SIGS.items():
     _f = getattr(lib, _n)

@@ -154,3 +154,92 @@ print('OK', len(mapped))
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300,
                        env=dict(os.environ, B200SP_NO_AUTOBUILD='1'))
     assert r.returncode == 0 and 'OK 306' in r.stdout, r.stdout + r.stderr
+
+
+# ---- row f1: input pipeline (oracle + host logic) ---------------------------------------------------
+def test_resampler_restatement_is_bit_exact_vs_pillow():
+    """third-party arithmetic (Pillow's 8-bit BILINEAR resize, used through T.resized_crop): the restatement against
+    the library itself, up- and down-scaling, one-axis-only, identity, RGB and grey."""
+    from PIL import Image
+    from oracle import transforms as ot
+    rng = np.random.default_rng(0)
+    for H, W, oh, ow, C in [(300, 300, 224, 224, 3), (1200, 1100, 224, 224, 1), (97, 101, 224, 224, 3), (224, 500, 224, 224, 1),
+                            (500, 224, 224, 224, 3), (224, 224, 224, 224, 3), (640, 481, 227, 227, 1), (50, 1000, 224, 224, 3)]:
+        img = rng.integers(0, 256, (H, W, C), dtype=np.uint8)
+        pil = Image.fromarray(img if C == 3 else img[:, :, 0]).resize((ow, oh), Image.BILINEAR)
+        ref = np.asarray(pil).reshape(oh, ow, C)
+        assert np.array_equal(ot.pil_resize_bilinear_u8(img, oh, ow), ref), (H, W, oh, ow, C)
+
+
+def _replay_case(case):
+    from oracle import transforms as ot
+    from oracle.make_golden_transforms import FRAME_HW, synth_frame, synth_keypoints
+    seed, bbox, p, is_train, model = case
+    H, W = FRAME_HW
+    frame = np.repeat(synth_frame(seed)[:, :, None], 3, 2)
+    kp = synth_keypoints(seed, bbox)
+    gen = torch.Generator().manual_seed(seed)
+    size = (224, 224) if model == 'krn' else (227, 227)
+    dec = dict(rot=0, flip=0, bc=None, noise=None)
+    if model == 'krn':
+        u = [torch.rand(1, generator=gen) for _ in range(3)] if is_train else None
+        box = ot.random_crop_box(bbox, W, H, is_train, u)
+        k, bb = ot.crop_keypoints(kp, box), np.array(box, np.float32)
+    else:
+        box = ot.resize_crop_box(bbox, W, H)
+        k, bb = torch.as_tensor(kp), np.array(bbox, np.float32)
+    img = ot.crop_resize_to_tensor(frame, box, size)
+    if is_train and model == 'krn':
+        dec = ot.draw_augment(p, img.shape, gen)
+        img, k = ot.apply_augment(img, k, **dec)
+    return img, bb, k, box, dec
+
+
+def test_transforms_oracle_replays_reference_bit_exact(golden_dir):
+    from oracle.make_golden_transforms import CASES
+    g = np.load(os.path.join(golden_dir, 'transforms.npz'))
+    fired = set()
+    for case in CASES:
+        img, bb, k, box, dec = _replay_case(case)
+        s = case[0]
+        assert np.array_equal(img.numpy(), g['img%d' % s]), s
+        assert np.array_equal(bb, g['bbox%d' % s]) and np.array_equal(k.numpy(), g['kpt%d' % s]), s
+        fired |= {n for n in ('rot', 'flip') if dec[n]} | {n for n in ('bc', 'noise') if dec[n] is not None}
+    assert fired == {'rot', 'flip', 'bc', 'noise'}          # the fixture exercises every augmentation
+
+
+def test_host_sampler_follows_reference_draws():
+    """datasets/transforms.py (product host code) draws the same decisions as the oracle replay of the reference stream."""
+    from oracle import transforms as ot
+    from oracle.make_golden_transforms import CASES, FRAME_HW
+    from speedplusbaseline_b200.datasets import transforms as dt
+    H, W = FRAME_HW
+    for seed, bbox, p, is_train, model in CASES:
+        if model != 'krn':
+            continue
+        g1, g2 = torch.Generator().manual_seed(seed), torch.Generator().manual_seed(seed)
+        box = dt.sample_crop_box(bbox, W, H, is_train, g1)
+        u = [torch.rand(1, generator=g2) for _ in range(3)] if is_train else None
+        assert box == ot.random_crop_box(bbox, W, H, is_train, u)
+        if is_train:
+            rot, flip, bc, a, b, std = dt.sample_augment(p, g1)
+            d = ot.draw_augment(p, (3, 224, 224), g2)
+            assert (rot, flip, bool(bc), std > 0) == (d['rot'], d['flip'], d['bc'] is not None, d['noise'] is not None)
+            if bc:
+                assert a == float(d['bc'][0]) and b == float(d['bc'][1])
+
+
+def test_dest_index_matches_torch_rot90_and_flip():
+    from speedplusbaseline_b200.datasets.transforms import dest_index
+    n = 5
+    x = torch.arange(n * n).reshape(1, n, n)
+    for rot in range(4):
+        for flip in range(3):
+            ref = torch.rot90(x, rot, (1, 2)) if rot else x
+            ref = ref.flip(2) if flip == 1 else (ref.flip(1) if flip == 2 else ref)
+            out = torch.empty_like(x)
+            for sy in range(n):
+                for sx in range(n):
+                    i, j = dest_index(sy, sx, n, n, rot, flip)
+                    out[0, i, j] = x[0, sy, sx]
+            assert torch.equal(out, ref), (rot, flip)

@@ -222,3 +222,159 @@ def test_valid_spn_batched_top_classes():
     ow, oi = postproc.spn_top_classes(r.cpu().numpy(), 5)
     assert (np.stack(rec['qs'])[:, :, 0] / 4 == oi).all()
     np.testing.assert_allclose(np.stack(rec['w']), ow, rtol=1e-4)      # two forwards: split-K fp32 atomics reorder
+
+
+# ---- row f1: input pipeline on the device -----------------------------------------------------------
+def _aug(box, dec=None, std=0.0, seed=1):
+    dec = dec or dict(rot=0, flip=0, bc=None)
+    bc = dec.get('bc')
+    return L.Aug(box[0], box[1], box[2], box[3], dec['rot'], dec['flip'], 1 if bc is not None else 0,
+                 float(bc[0]) if bc is not None else 1.0, float(bc[1]) if bc is not None else 0.0, std, seed, 0)
+
+
+def _replay(case):
+    """decisions + expected tensors of one golden case, replayed through the oracle (test_next_rows_cpu pins this replay
+    to the reference bit for bit)."""
+    from oracle import transforms as ot
+    from oracle.make_golden_transforms import FRAME_HW, synth_frame, synth_keypoints
+    seed, bbox, p, is_train, model = case
+    H, W = FRAME_HW
+    grey = synth_frame(seed)
+    kp = synth_keypoints(seed, bbox)
+    gen = torch.Generator().manual_seed(seed)
+    size = (224, 224) if model == 'krn' else (227, 227)
+    dec = dict(rot=0, flip=0, bc=None, noise=None)
+    if model == 'krn':
+        u = [torch.rand(1, generator=gen) for _ in range(3)] if is_train else None
+        box = ot.random_crop_box(bbox, W, H, is_train, u)
+        k = ot.crop_keypoints(kp, box)
+    else:
+        box = ot.resize_crop_box(bbox, W, H)
+        k = torch.as_tensor(kp)
+    img = ot.crop_resize_to_tensor(np.repeat(grey[:, :, None], 3, 2), box, size)
+    if is_train and model == 'krn':
+        dec = ot.draw_augment(p, img.shape, gen)
+    nonoise = {k2: v for k2, v in dec.items() if k2 != 'noise'}
+    img_nn, k = ot.apply_augment(img, k, **nonoise)
+    return grey, kp, box, dec, img_nn, k
+
+
+@pytest.mark.parametrize('channels', [1, 3])
+def test_input_pipeline_bit_exact_vs_reference_transforms(golden_dir, channels):
+    from oracle.make_golden_transforms import CASES
+    from speedplusbaseline_b200.datasets.transforms import DeviceTransforms
+    g = np.load(os.path.join(golden_dir, 'transforms.npz'))
+    for model, size in (('krn', (224, 224)), ('spn', (227, 227))):
+        cases = [c for c in CASES if c[4] == model]
+        rp = [_replay(c) for c in cases]
+        frames = torch.from_numpy(np.stack([r[0] for r in rp]))
+        if channels == 3:
+            frames = frames.unsqueeze(-1).repeat(1, 1, 1, 3)
+        tf = DeviceTransforms(model, size, device='cuda')
+        augs = [_aug(r[2], r[3]) for r in rp]
+        out, kout = tf.apply(frames, augs, np.stack([r[1] for r in rp]), normalize_kpts=model == 'krn')
+        torch.cuda.synchronize()
+        assert tf.status() == 0
+        for i, (c, r) in enumerate(zip(cases, rp)):
+            assert torch.equal(out[i].cpu(), r[4]), ('image', c[0])                    # vs the oracle (noise switched off)
+            assert torch.equal(kout[i].cpu(), r[5]), ('keypoints', c[0])
+            assert np.array_equal(kout[i].cpu().numpy(), g['kpt%d' % c[0]])
+            if r[3]['noise'] is None:                                                    # no noise drawn: the reference output itself
+                assert np.array_equal(out[i].cpu().numpy(), g['img%d' % c[0]]), ('golden', c[0])
+
+
+def test_input_pipeline_full_size_frames_vs_oracle():
+    """SPEED+ geometry: 1200x1920 grey frames, RoIs from tiny to the whole frame height, every rotation / flip."""
+    from oracle import transforms as ot
+    from speedplusbaseline_b200.datasets.transforms import DeviceTransforms
+    rng = np.random.default_rng(11)
+    H, W, B = 1200, 1920, 6
+    frames = rng.integers(0, 256, (B, H, W), dtype=np.uint8)
+    boxes = [(0, 1200, 0, 1200), (700, 1920, 0, 1200), (900, 1000, 500, 601), (13, 237, 977, 1200), (300, 1500, 100, 1150), (1000, 1224, 400, 624)]
+    decs = [dict(rot=i % 4, flip=i % 3, bc=(0.5 + 0.3 * i, 0.05 * (i - 2)) if i % 2 else None) for i in range(B)]
+    tf = DeviceTransforms('krn', (224, 224), device='cuda')
+    out, _ = tf.apply(torch.from_numpy(frames), [_aug(b, d) for b, d in zip(boxes, decs)])
+    torch.cuda.synchronize()
+    assert tf.status() == 0
+    for i in range(B):
+        img = ot.crop_resize_to_tensor(np.repeat(frames[i][:, :, None], 3, 2), boxes[i], (224, 224))
+        img, _ = ot.apply_augment(img, torch.zeros(2, 1), **decs[i])
+        assert torch.equal(out[i].cpu(), img), i
+
+
+def test_input_pipeline_noise_statistics():
+    """GaussianNoise :101-112 is N(0, (25/255)^2) per element; the device generator is checked statistically."""
+    from speedplusbaseline_b200.datasets.transforms import DeviceTransforms
+    frames = torch.full((2, 300, 300), 128, dtype=torch.uint8)
+    tf = DeviceTransforms('krn', (224, 224), device='cuda')
+    std = 25 / 255
+    a1, _ = tf.apply(frames, [_aug((0, 300, 0, 300), std=std, seed=5), _aug((0, 300, 0, 300), std=std, seed=6)])
+    a2, _ = tf.apply(frames, [_aug((0, 300, 0, 300), std=std, seed=5), _aug((0, 300, 0, 300), std=0.0)])
+    torch.cuda.synchronize()
+    base = 128 / 255
+    assert torch.equal(a2[1].cpu(), torch.full((3, 224, 224), base))
+    assert torch.equal(a1[0], a2[0])                                   # same seed, same noise
+    n = (a1.double().cpu() - base)                                      # 0.5 +- 5 sigma stays inside [0,1]: no clamping
+    N = n[0].numel()
+    for i in range(2):
+        assert abs(float(n[i].mean())) < 5 * std / N ** 0.5
+        assert abs(float(n[i].std()) / std - 1) < 0.01
+        assert abs(float((n[i] ** 4).mean()) / std ** 4 - 3) < 0.1      # Gaussian kurtosis
+    c = np.corrcoef(n[0].reshape(3, -1).numpy())
+    assert abs(c[0, 1]) < 0.02 and abs(c[1, 2]) < 0.02                  # channels get independent noise
+    assert abs(np.corrcoef(n[0].reshape(-1).numpy(), n[1].reshape(-1).numpy())[0, 1]) < 0.02    # and so do seeds
+
+
+def test_input_pipeline_guards_and_errors():
+    frames = torch.randint(0, 256, (1, 64, 64, 1), dtype=torch.uint8, device='cuda')
+    aug = torch.frombuffer(bytearray(bytes((L.Aug * 1)(L.Aug(0, 64, 0, 64, 0, 0, 0, 1.0, 0.0, 0.0, 1, 0)))), dtype=torch.uint8).cuda()
+    oh = ow = 8                                       # scale 8 -> 17 taps needed
+    status = torch.zeros(1, dtype=torch.int32, device='cuda')
+    out = torch.full((1, 3, oh, ow), -1.0, device='cuda')
+
+    def run(ks, tmp_rows, C_=1, odd=0, oh_=oh):
+        coef = torch.zeros(2 * 8 * (2 + ks), dtype=torch.int32, device='cuda')
+        tmp = torch.zeros(max(1, tmp_rows) * ow, dtype=torch.uint8, device='cuda')
+        return L.lib.b200sp_input_pipeline(frames.data_ptr(), 1, 64, 64, C_, aug.data_ptr(), coef.data_ptr(), tmp.data_ptr(), tmp_rows,
+                                           ks, out.data_ptr(), oh_, ow, odd, status.data_ptr(), sp())
+    assert run(17, 64) == 0
+    torch.cuda.synchronize()
+    assert int(status.item()) == 0 and float(out.min()) >= 0.0
+    assert run(5, 64) == 0                            # too few taps: flagged, truncated, in bounds
+    torch.cuda.synchronize()
+    assert int(status.item()) & 2
+    status.zero_()
+    assert run(17, 32) == 0                           # temp too small for the crop: flagged, zeros
+    torch.cuda.synchronize()
+    assert int(status.item()) & 1 and float(out.abs().max()) == 0.0
+    assert run(17, 64, C_=2) == -22 and run(2, 64) == -22 and run(17, 64, odd=1, oh_=4) == -22
+    from speedplusbaseline_b200.datasets.transforms import DeviceTransforms
+    tf = DeviceTransforms('krn', (8, 8), device='cuda')
+    with pytest.raises(ValueError):
+        tf.apply(frames, [L.Aug(0, 65, 0, 64, 0, 0, 0, 1.0, 0.0, 0.0, 1, 0)])
+    with pytest.raises(TypeError):
+        tf.apply(frames.float(), [L.Aug(0, 64, 0, 64, 0, 0, 0, 1.0, 0.0, 0.0, 1, 0)])
+
+
+def test_device_transforms_feed_the_training_step():
+    """build_transforms(...) output is what the fused KRN step consumes: frames -> images/keypoints -> one train step."""
+    from speedplusbaseline_b200.datasets.transforms import build_transforms
+    from speedplusbaseline_b200.nets.park2019 import KeypointRegressionNet
+    from speedplusbaseline_b200.optim import FusedAdamW
+    from speedplusbaseline_b200.core.trainer import KRNTrainStep
+    rng = np.random.default_rng(2)
+    B, H, W = 4, 600, 960
+    frames = torch.from_numpy(rng.integers(0, 256, (B, H, W), dtype=np.uint8)).pin_memory()
+    bbox = np.array([[100, 400, 50, 300], [300, 900, 100, 580], [10, 200, 20, 120], [500, 800, 200, 590]], np.float32)
+    kp = np.stack([np.stack([rng.uniform(b[0], b[1], 11), rng.uniform(b[2], b[3], 11)]) for b in bbox]).astype(np.float32)
+    tf = build_transforms('krn', (224, 224), p_aug=0.5, is_train=True, device='cuda', generator=torch.Generator().manual_seed(3))
+    images, bb, kpts = tf(frames, bbox, kp)
+    torch.cuda.synchronize()
+    assert tf.status() == 0 and images.shape == (B, 3, 224, 224) and kpts.shape == (B, 2, 11) and bb.shape == (B, 4)
+    assert float(images.min()) >= 0.0 and float(images.max()) <= 1.0 and float(images.std()) > 0.05
+    m = KeypointRegressionNet(11, device='cuda', seed=1)
+    m.train()
+    opt = FusedAdamW(m._store, m.parameters(), lr=1e-3, weight_decay=0.01, clip_mode=1)
+    loss3 = KRNTrainStep(m, opt, use_graph=False).step(images, kpts.contiguous())
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss3).all() and float(loss3[0]) > 0
