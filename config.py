@@ -52,6 +52,9 @@ _FLAGS = [
     ('--reference_root', dict(type=str, default=os.environ.get('SPEEDPLUS_REFERENCE', ''),
                               help='checkout of tpark94/speedplusbaseline providing src.datasets / src.core.inference')),
     ('--no_graph', dict(dest='use_graph', action='store_false', default=True)),
+    ('--device_transforms', dict(action='store_true', default=False,
+                                 help='decode-only DataLoader workers + the transform stack (crop/resize/augment) on the GPU '
+                                      '(speedplusbaseline_b200/datasets); KRN train/test and SPN test')),
 ]
 
 

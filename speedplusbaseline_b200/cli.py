@@ -66,6 +66,9 @@ def make_loaders(cfg, specs):
     (src/datasets/build.py:45-66)."""
     if cfg.synthetic_data > 0:
         return [SyntheticLoader(cfg, cfg.synthetic_data, labels=s.get('load_labels', True), seed=i) for i, s in enumerate(specs)]
+    if getattr(cfg, 'device_transforms', False) and torch.cuda.is_available() and cfg.use_cuda:
+        from .datasets.raw import make_dataloader as make_device_dataloader
+        return [make_device_dataloader(cfg, device=select_device(cfg), **s) for s in specs]
     reference_modules(cfg)
     from src.datasets.build import make_dataloader
     return [make_dataloader(cfg, **s) for s in specs]

@@ -159,6 +159,10 @@ class DevicePrefetcher:
             self.bufs[slot] = [torch.empty(t.shape, dtype=torch.float32, device=self.device) for t in batch]
         if self.consumed[slot] is not None:
             self.stream.wait_event(self.consumed[slot])
+        if any(t.is_cuda for t in batch):
+            # batches produced ON the device (datasets/raw.py:DeviceBatchLoader runs the transform stack on the current
+            # stream): the copy stream must not read them before those kernels have finished
+            self.stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.stream):
             for b, t in zip(self.bufs[slot], batch):
                 b.copy_(t, non_blocking=True)

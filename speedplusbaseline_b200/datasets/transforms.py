@@ -85,6 +85,53 @@ def sample_augment(p, gen=None):
     return rot, flip, bc, a, b, std
 
 
+def sample_batch(bbox, org_w, org_h, model_name, is_train, p, gen=None, u=None):
+    """Decisions for a whole batch from ONE block of uniforms u [B, 11] (drawn here unless given):
+    columns 0-2 RoI enlargement / x shift / y shift (RandomCrop :136-142); 3 rotate?, 4 which quarter turn (Rotate :41:
+    randint(1,4) == 1 + floor(3u)); 5 flip?, 6 direction (Flip :61); 7 brightness-contrast?, 8-9 its alpha / beta draws
+    (:89-94); 10 noise? (RandomApply :209).  Float32 torch arithmetic in the reference's operation order, so a row given the
+    reference's own uniforms reproduces `sample_crop_box` and the brightness / contrast factors of `sample_augment` exactly
+    (tests/test_next_rows_cpu.py)."""
+    B = bbox.shape[0]
+    if u is None:
+        u = torch.rand(B, 11, generator=gen)
+    u = u.to(torch.float32)
+    bb = torch.from_numpy(np.ascontiguousarray(bbox, dtype=np.float32))
+    xmin, xmax, ymin, ymax = bb[:, 0], bb[:, 1], bb[:, 2], bb[:, 3]
+    if model_name == 'krn':
+        w, h = xmax - xmin, ymax - ymin
+        x, y = xmin + w / 2.0, ymin + h / 2.0
+        roi = torch.maximum(w, h)
+        if is_train:
+            roi = (1 + 0.5 * u[:, 0]) * roi
+            fx = 0.2 * (u[:, 1] * 2 - 1) * roi
+            fy = 0.2 * (u[:, 2] * 2 - 1) * roi
+        else:
+            roi = (1 + 0.2) * roi
+            fx = fy = torch.zeros(B)
+        x0 = (x - roi / 2.0 + fx).to(torch.int64).clamp_(min=0)           # int(): truncation toward zero
+        x1 = (x + roi / 2.0 + fx).to(torch.int64).clamp_(max=org_w)
+        y0 = (y - roi / 2.0 + fy).to(torch.int64).clamp_(min=0)
+        y1 = (y + roi / 2.0 + fy).to(torch.int64).clamp_(max=org_h)
+    else:                                                                   # ResizeCrop :176-184
+        x0, x1 = xmin.to(torch.int64).clamp_(min=0), xmax.to(torch.int64).clamp_(max=org_w)
+        y0, y1 = ymin.to(torch.int64).clamp_(min=0), ymax.to(torch.int64).clamp_(max=org_h)
+    box = torch.stack([x0, x1, y0, y1], 1).tolist()
+    rot, flip, bc = [0] * B, [0] * B, [0] * B
+    a, b, std, seed = [1.0] * B, [0.0] * B, [0.0] * B, list(range(1, B + 1))
+    if is_train and model_name == 'krn':
+        rot = torch.where(u[:, 3] < p, 1 + (u[:, 4] * 3).to(torch.int64).clamp_(max=2), torch.zeros(B, dtype=torch.int64)).tolist()
+        flip = torch.where(u[:, 5] < p, torch.where(u[:, 6] < 0.5, 1, 2), torch.zeros(B, dtype=torch.int64)).tolist()
+        la, lb = torch.tensor((0.5, 2.0)).log(), torch.tensor((-25, 25)) / 255
+        on = u[:, 7] < p
+        bc = on.to(torch.int64).tolist()
+        a = torch.where(on, (u[:, 8] * (la[1] - la[0]) + la[0]).exp(), torch.ones(B)).tolist()
+        b = torch.where(on, u[:, 9] * (lb[1] - lb[0]) + lb[0], torch.zeros(B)).tolist()
+        std = torch.where(u[:, 10] < p, torch.full((B,), 25 / 255), torch.zeros(B)).tolist()
+        seed = torch.randint(0, 2 ** 31 - 1, (B,), generator=gen).tolist()
+    return dict(box=[tuple(r) for r in box], rot=rot, flip=flip, bc=bc, a=a, b=b, std=std, seed=seed)
+
+
 class DeviceTransforms:
     def __init__(self, model_name, input_size, p_aug=0.5, is_train=True, device=None, generator=None):
         assert model_name in ('krn', 'spn')
@@ -99,21 +146,17 @@ class DeviceTransforms:
 
     # decisions for a batch -> list of L.Aug
     def sample(self, bbox, org_w, org_h):
-        augs, boxes = [], []
-        for bb in np.asarray(bbox, np.float32):
-            if self.model_name == 'krn':
-                x0, x1, y0, y1 = sample_crop_box(bb, org_w, org_h, self.is_train, self.gen)
-            else:                                        # ResizeCrop :176-184
-                x0, x1, y0, y1 = max(0, int(bb[0])), min(org_w, int(bb[1])), max(0, int(bb[2])), min(org_h, int(bb[3]))
-            rot = flip = bc = 0
-            a, b, std = 1.0, 0.0, 0.0
-            if self.is_train and self.model_name == 'krn':
-                rot, flip, bc, a, b, std = sample_augment(self.p, self.gen)
-            self._seed = (self._seed + 1) & 0xFFFFFFFF
-            seed = int(torch.randint(0, 2 ** 31 - 1, (1,), generator=self.gen)) if std > 0 else self._seed
-            augs.append(L.Aug(x0, x1, y0, y1, rot, flip, bc, a, b, std, seed, 0))
-            boxes.append((x0, x1, y0, y1))
-        return augs, boxes
+        """one batch of decisions.  Vectorised (`sample_batch`): the per-sample functions above follow the reference's RNG
+        draw ORDER (kept for the parity tests); here every uniform of the batch comes from one torch.rand call and goes through
+        the same float32 formulas -- same distributions, ~50x less host time at bs=48 (the reference's DataLoader workers each
+        have their own stream anyway, so there is no batch-level stream to match)."""
+        dec = sample_batch(np.asarray(bbox, np.float32), org_w, org_h, self.model_name, self.is_train, self.p, self.gen)
+        augs = []
+        for i in range(len(dec['box'])):
+            x0, x1, y0, y1 = dec['box'][i]
+            augs.append(L.Aug(x0, x1, y0, y1, dec['rot'][i], dec['flip'][i], dec['bc'][i], dec['a'][i], dec['b'][i],
+                              dec['std'][i], dec['seed'][i], 0))
+        return augs, dec['box']
 
     def _buf(self, name, numel, dtype):
         t = self._scratch.get(name)

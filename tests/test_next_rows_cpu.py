@@ -243,3 +243,87 @@ def test_dest_index_matches_torch_rot90_and_flip():
                     i, j = dest_index(sy, sx, n, n, rot, flip)
                     out[0, i, j] = x[0, sy, sx]
             assert torch.equal(out, ref), (rot, flip)
+
+
+def test_vectorised_sampler_equals_per_sample_formulas():
+    """sample_batch (one block of uniforms per batch) == the per-sample reference-order functions fed the same uniforms."""
+    from oracle import transforms as ot
+    from speedplusbaseline_b200.datasets import transforms as dt
+    g = torch.Generator().manual_seed(5)
+    B, W, H = 64, 1920, 1200
+    c = torch.rand(B, 2, generator=g) * torch.tensor([1920., 1200.])
+    sz = torch.rand(B, 2, generator=g) * 900 + 20
+    bbox = torch.stack([c[:, 0] - sz[:, 0] / 2, c[:, 0] + sz[:, 0] / 2, c[:, 1] - sz[:, 1] / 2, c[:, 1] + sz[:, 1] / 2], 1).numpy()
+    u = torch.rand(B, 11, generator=g)
+    for is_train in (True, False):
+        d = dt.sample_batch(bbox, W, H, 'krn', is_train, 0.5, u=u)
+        for i in range(B):
+            assert d['box'][i] == ot.random_crop_box(bbox[i], W, H, is_train, [u[i, 0:1], u[i, 1:2], u[i, 2:3]]), i
+        if is_train:
+            la, lb = torch.tensor((0.5, 2.0)).log(), torch.tensor((-25, 25)) / 255
+            for i in range(B):
+                assert d['rot'][i] == (1 + min(2, int(u[i, 4] * 3)) if u[i, 3] < 0.5 else 0)
+                assert d['flip'][i] == ((1 if u[i, 6] < 0.5 else 2) if u[i, 5] < 0.5 else 0)
+                if u[i, 7] < 0.5:
+                    assert d['bc'][i] == 1
+                    assert np.float32(d['a'][i]) == np.float32(float((u[i, 8:9] * (la[1] - la[0]) + la[0]).exp()))
+                    assert np.float32(d['b'][i]) == np.float32(float(u[i, 9:10] * (lb[1] - lb[0]) + lb[0]))
+                else:
+                    assert (d['bc'][i], d['a'][i], d['b'][i]) == (0, 1.0, 0.0)
+                assert (d['std'][i] > 0) == bool(u[i, 10] < 0.5)
+            assert {0, 1, 2, 3} == set(d['rot']) and {0, 1, 2} == set(d['flip'])
+        else:
+            assert set(d['rot']) == {0} and set(d['std']) == {0.0}
+    s = dt.sample_batch(bbox, W, H, 'spn', False, 0.0, u=u)
+    for i in range(B):
+        assert s['box'][i] == ot.resize_crop_box(bbox[i], W, H)
+
+
+def _write_split(root, n, hw=(120, 160), K=11, rgb_index=None):
+    """a miniature SPEED+-style tree: <root>/speedplus/synthetic/{images,splits_krn/train.csv} (+ lightbox for tests)."""
+    from PIL import Image
+    import pandas as pd
+    rng = np.random.default_rng(0)
+    rows = []
+    for dom, csv in (('synthetic', 'train.csv'), ('lightbox', 'lightbox.csv')):
+        os.makedirs(os.path.join(root, 'speedplus', dom, 'images'), exist_ok=True)
+        os.makedirs(os.path.join(root, 'speedplus', dom, 'splits_krn'), exist_ok=True)
+        rows = []
+        for i in range(n):
+            arr = rng.integers(0, 256, hw, dtype=np.uint8)
+            rel = os.path.join(dom, 'images', 'img%03d.png' % i)
+            im = Image.fromarray(arr)
+            if rgb_index == i:
+                im = im.convert('RGB')
+            im.save(os.path.join(root, 'speedplus', rel))
+            bbox = [20 + i, 100 + i, 10 + i, 90 + i]
+            pose = list(rng.normal(size=7))
+            kp = list(rng.uniform(20, 100, 2 * K))
+            rows.append([rel] + bbox + pose + kp)
+        pd.DataFrame(rows).to_csv(os.path.join(root, 'speedplus', dom, 'splits_krn', csv), header=False, index=False)
+    return rows
+
+
+def test_raw_frame_dataset_reads_reference_csv_layout(tmp_path):
+    from types import SimpleNamespace
+    from PIL import Image
+    from speedplusbaseline_b200.datasets.raw import RawFrameDataset
+    rows = _write_split(str(tmp_path), 3, rgb_index=1)
+    cfg = SimpleNamespace(dataroot=str(tmp_path), dataname='speedplus', num_keypoints=11, model_name='krn', train_domain='synthetic',
+                          test_domain='lightbox', train_csv='train.csv', test_csv='lightbox.csv')
+    tr = RawFrameDataset(cfg, is_train=True, is_source=True, load_labels=True)
+    assert len(tr) == 3
+    frame, bbox, kp, q, t = tr[2]
+    assert frame.dtype == torch.uint8 and tuple(frame.shape) == (120, 160) and tuple(kp.shape) == (2, 11)
+    ref = np.array(Image.open(os.path.join(str(tmp_path), 'speedplus', 'synthetic', 'images', 'img002.png')))
+    assert np.array_equal(frame.numpy(), ref)
+    assert tuple(tr[1][0].shape) == (120, 160, 3)                               # non-grey files go through RGB like upstream
+    te = RawFrameDataset(cfg, is_train=False, is_source=False, load_labels=True)
+    f2, b2, k2, q2, t2 = te[0]
+    assert np.allclose(b2.numpy(), rows[0][1:5]) and np.allclose(q2.numpy(), rows[0][5:9], atol=1e-6)
+    assert np.allclose(t2.numpy(), rows[0][9:12], atol=1e-6) and float(k2.abs().sum()) == 0.0
+    # keypoint columns: kx1, ky1, kx2, ... -> [2, K] (Park2019KRNDataset.py:92-93)
+    tgt = RawFrameDataset(cfg, is_train=True, is_source=False, load_labels=False)
+    assert len(tgt) == 3
+    with pytest.raises(AssertionError):
+        RawFrameDataset(cfg, is_train=True, is_source=False, load_labels=True)

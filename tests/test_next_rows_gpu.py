@@ -378,3 +378,53 @@ def test_device_transforms_feed_the_training_step():
     loss3 = KRNTrainStep(m, opt, use_graph=False).step(images, kpts.contiguous())
     torch.cuda.synchronize()
     assert torch.isfinite(loss3).all() and float(loss3[0]) > 0
+
+
+def test_device_batch_loader_drives_the_reference_epoch_loop(tmp_path):
+    """decode-only dataset -> DeviceBatchLoader -> train_single_epoch_krn (unchanged loop, DevicePrefetcher included)."""
+    from types import SimpleNamespace
+    from test_next_rows_cpu import _write_split
+    from speedplusbaseline_b200.datasets.raw import make_dataloader
+    from speedplusbaseline_b200.nets.park2019 import KeypointRegressionNet
+    from speedplusbaseline_b200.optim import FusedAdamW
+    from speedplusbaseline_b200.core.trainer import train_single_epoch_krn
+    _write_split(str(tmp_path), 8, hw=(300, 400))
+    cfg = SimpleNamespace(dataroot=str(tmp_path), dataname='speedplus', num_keypoints=11, model_name='krn', train_domain='synthetic',
+                          test_domain='lightbox', train_csv='train.csv', test_csv='lightbox.csv', batch_size=4, num_workers=0,
+                          input_shape=(224, 224), texture_ratio=0.5, use_graph=False)
+    dev = torch.device('cuda')
+    loader = make_dataloader(cfg, is_train=True, is_source=True, load_labels=True, device=dev, generator=_g(1))
+    assert len(loader) == 2
+    m = KeypointRegressionNet(11, device='cuda', seed=1)
+    p0 = m._store.params.clone()
+    opt = FusedAdamW(m._store, m.parameters(), lr=1e-3, weight_decay=0.01, clip_mode=1)
+    train_single_epoch_krn(1, cfg, m, loader, opt, None, dev)
+    torch.cuda.synchronize()
+    assert loader.tf.status() == 0
+    assert torch.isfinite(m._store.params).all() and float((m._store.params - p0).abs().max()) > 0
+    assert int(m._store.nbt[0]) == 2
+    test_loader = make_dataloader(cfg, is_train=False, is_source=False, load_labels=True, device=dev)
+    images, bbox, q, t = next(iter(test_loader))
+    assert images.shape == (1, 3, 224, 224) and bbox.shape == (1, 4) and q.shape == (1, 4) and t.shape == (1, 3)
+
+
+@pytest.mark.parametrize('name', ['sgd', 'rmsprop', 'adam'])
+def test_fused_optimizers_inside_the_captured_krn_step(name):
+    """get_optimizer(--optimizer sgd|rmsprop|adam) -> CUDA-graph-captured KRN step == the eager step, trajectory finite."""
+    from types import SimpleNamespace
+    from speedplusbaseline_b200.nets.build import get_optimizer
+    from speedplusbaseline_b200.nets.park2019 import KeypointRegressionNet
+    from speedplusbaseline_b200.core.trainer import KRNTrainStep
+    cfg = SimpleNamespace(optimizer=name, lr=1e-3, momentum=0.9, weight_decay=0.01, model_name='krn', dann=False)
+    x, y = torch.rand(4, 3, 224, 224, generator=_g(1)).cuda(), torch.rand(4, 2, 11, generator=_g(2)).cuda()
+    losses = []
+    for use_graph in (True, False):
+        m = KeypointRegressionNet(11, device='cuda', seed=3)
+        m.train()
+        opt = get_optimizer(cfg, m)
+        assert type(opt).__name__ == {'sgd': 'FusedSGD', 'rmsprop': 'FusedRMSprop', 'adam': 'FusedAdam'}[name]
+        st = KRNTrainStep(m, opt, use_graph=use_graph)
+        losses.append([float(st.step(x, y)[0]) for _ in range(3)])
+        assert torch.isfinite(m._store.params).all()
+    assert all(np.isfinite(losses[0])) and losses[0][2] != losses[0][0]
+    np.testing.assert_allclose(losses[0], losses[1], rtol=2e-3)      # graph replay == eager (fp32 atomics reorder only)
