@@ -410,21 +410,29 @@ def test_device_batch_loader_drives_the_reference_epoch_loop(tmp_path):
 
 @pytest.mark.parametrize('name', ['sgd', 'rmsprop', 'adam'])
 def test_fused_optimizers_inside_the_captured_krn_step(name):
-    """get_optimizer(--optimizer sgd|rmsprop|adam) -> CUDA-graph-captured KRN step == the eager step, trajectory finite."""
+    """get_optimizer(--optimizer sgd|rmsprop|adam) -> CUDA-graph-captured KRN step == the eager step.
+    lr is small on purpose: RMSprop / Adam move EVERY parameter by ~lr per step whatever its gradient, and at lr 1e-3 a
+    randomly initialised KRN leaves the basin within two steps (loss 12 -> 4e4, measured), where fp32 summation-order noise
+    between two runs is amplified to percents and a trajectory comparison says nothing."""
     from types import SimpleNamespace
     from speedplusbaseline_b200.nets.build import get_optimizer
     from speedplusbaseline_b200.nets.park2019 import KeypointRegressionNet
     from speedplusbaseline_b200.core.trainer import KRNTrainStep
-    cfg = SimpleNamespace(optimizer=name, lr=1e-3, momentum=0.9, weight_decay=0.01, model_name='krn', dann=False)
+    cfg = SimpleNamespace(optimizer=name, lr=1e-5, momentum=0.9, weight_decay=0.01, model_name='krn', dann=False)
     x, y = torch.rand(4, 3, 224, 224, generator=_g(1)).cuda(), torch.rand(4, 2, 11, generator=_g(2)).cuda()
-    losses = []
+    losses, params = [], []
     for use_graph in (True, False):
         m = KeypointRegressionNet(11, device='cuda', seed=3)
         m.train()
+        p0 = m._store.params.clone()
         opt = get_optimizer(cfg, m)
         assert type(opt).__name__ == {'sgd': 'FusedSGD', 'rmsprop': 'FusedRMSprop', 'adam': 'FusedAdam'}[name]
         st = KRNTrainStep(m, opt, use_graph=use_graph)
         losses.append([float(st.step(x, y)[0]) for _ in range(3)])
         assert torch.isfinite(m._store.params).all()
+        params.append(m._store.params.clone())
+        assert float((params[-1] - p0).abs().max()) > 0              # the captured update really ran
     assert all(np.isfinite(losses[0])) and losses[0][2] != losses[0][0]
-    np.testing.assert_allclose(losses[0], losses[1], rtol=2e-3)      # graph replay == eager (fp32 atomics reorder only)
+    np.testing.assert_allclose(losses[0], losses[1], rtol=1e-2)      # graph replay == eager (fp32 atomics reorder only)
+    assert abs(losses[0][0] - losses[1][0]) <= 1e-4 * abs(losses[1][0])          # first step: same weights, same batch
+    assert rel(params[0], params[1]) < 1e-3
