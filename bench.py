@@ -142,7 +142,6 @@ def secondary_workloads(dev, stepper, d_img, d_tgt, k=8):
     """The other BASELINE.json configs on ONE GPU, device-resident inputs, CUDA events (ms per step, images/s):
     configs[2] KRN + style augmentation every step, configs[3] DANN step (48 source + 48 target), configs[4] SPN bs=32."""
     import torch
-    from oracle import ghiasi as ogh, synth                       # weights only (synthetic Ghiasi checkpoint)
     from speedplusbaseline_b200.styleaug.styleAugmentor import StyleAugmentor
     from speedplusbaseline_b200.nets.revgrad import RevGrad
     from speedplusbaseline_b200.nets.spn import SpacecraftPoseNet
@@ -150,10 +149,8 @@ def secondary_workloads(dev, stepper, d_img, d_tgt, k=8):
     from speedplusbaseline_b200.core.dann import DANNTrainStep
     from speedplusbaseline_b200.core.trainer import SPNTrainStep
     out = {}
-    g = torch.Generator().manual_seed(1)
-    cov = torch.randn(100, 100, generator=g)
-    state = dict(ghiasi=synth.synth_state_dict(ogh.ghiasi_shapes(), 7), mean=torch.randn(1, 100, generator=g),
-                 cov=(cov @ cov.t() / 100).numpy(), base=torch.randn(100, generator=g))
+    from speedplusbaseline_b200.styleaug.ghiasi import synthetic_state
+    state = synthetic_state(7)                                   # random Ghiasi weights + embedding statistics (no checkpoint files here)
     aug = StyleAugmentor(0.5, dev, state=state)
     ms = _time_steps(lambda: aug(d_img), 2, k)
     out['styleaug_forward_bs48'] = {'ms': ms, 'images_per_sec': BATCH / ms * 1e3, 'tflops_reference_flops': 15.434 * BATCH / ms}

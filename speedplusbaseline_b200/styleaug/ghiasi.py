@@ -26,6 +26,33 @@ def cond_sets():
     return out
 
 
+CONV_SPECS = ((0, 3, 32, 9), (1, 32, 64, 3), (2, 64, 128, 3), (8, 128, 64, 3), (9, 64, 32, 3), (10, 32, 3, 9))   # layer, Cin, Cout, k
+
+
+def param_shapes():
+    """state_dict key -> shape of the reference's `Ghiasi()` module (ghiasi.py:106-121; 84 tensors, the keys of
+    checkpoint_transformer.pth['state_dict_ghiasi'])."""
+    d = {}
+    for i, ci, co, k in CONV_SPECS:
+        d['layers.%d.conv.weight' % i], d['layers.%d.conv.bias' % i] = (co, ci, k, k), (co,)
+    for i in range(3, 8):
+        for j in ('1', '2'):
+            d['layers.%d.conv%s.weight' % (i, j)], d['layers.%d.conv%s.bias' % (i, j)] = (128, 128, 3, 3), (128,)
+    for pre, sfx, c in cond_sets():
+        for g in ('beta', 'gamma'):
+            d['%s.fc_%s%s.weight' % (pre, g, sfx)], d['%s.fc_%s%s.bias' % (pre, g, sfx)] = (c, 100), (c,)
+    return d
+
+
+def synthetic_state(seed=7):
+    """random stand-in for the style checkpoints (benchmarks / smoke runs on a box without the reference's files):
+    dict(ghiasi, mean, cov, base) as StyleAugmentor(state=...) takes it."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {k: 0.05 * torch.randn(shp, generator=g) for k, shp in sorted(param_shapes().items())}
+    cov = torch.randn(100, 100, generator=g)
+    return dict(ghiasi=sd, mean=torch.randn(1, 100, generator=g), cov=(cov @ cov.t() / 100).numpy(), base=torch.randn(100, generator=g))
+
+
 def plan_chunks(k, ps, Cin, Cp, Wq):
     """K-chunk list of the shifted GEMM.  Returns (chunks [(plane, c0, shift)], cols [[(kh, kw, c) | None] * 64])."""
     cbox = min(Cp, 64)

@@ -117,3 +117,15 @@ def test_get_optimizer_dispatch_and_unknown_model_asserts():
     from speedplusbaseline_b200.nets import build
     with pytest.raises(AssertionError):
         build.get_model(types.SimpleNamespace(model_name='resnet', dann=False))
+
+
+def test_ghiasi_param_table_matches_oracle_and_synthetic_state():
+    """styleaug/ghiasi.py:param_shapes (product) lists exactly the reference module's 84 tensors (oracle table, which is
+    pinned to the real checkpoint keys by the golden tests); synthetic_state feeds StyleAugmentor(state=...)."""
+    from oracle import ghiasi as og
+    from speedplusbaseline_b200.styleaug import ghiasi as pg
+    a, b = pg.param_shapes(), og.ghiasi_shapes()
+    assert set(a) == set(b) and all(tuple(a[k]) == tuple(b[k]) for k in b) and len(a) == 84
+    st = pg.synthetic_state(3)
+    assert set(st) == {'ghiasi', 'mean', 'cov', 'base'} and st['cov'].shape == (100, 100)
+    assert all(tuple(st['ghiasi'][k].shape) == tuple(a[k]) for k in a)
