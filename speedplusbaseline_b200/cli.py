@@ -66,12 +66,19 @@ def make_loaders(cfg, specs):
     (src/datasets/build.py:45-66)."""
     if cfg.synthetic_data > 0:
         return [SyntheticLoader(cfg, cfg.synthetic_data, labels=s.get('load_labels', True), seed=i) for i, s in enumerate(specs)]
-    if getattr(cfg, 'device_transforms', False) and torch.cuda.is_available() and cfg.use_cuda:
-        from .datasets.raw import make_dataloader as make_device_dataloader
-        return [make_device_dataloader(cfg, device=select_device(cfg), **s) for s in specs]
-    reference_modules(cfg)
-    from src.datasets.build import make_dataloader
-    return [make_dataloader(cfg, **s) for s in specs]
+    on_device = getattr(cfg, 'device_transforms', False) and torch.cuda.is_available() and cfg.use_cuda
+    out = []
+    for s in specs:
+        # SPN TRAINING batches carry soft attitude-class targets built by the reference's SPNDataset (SPNDataset.py:83-94):
+        # those loaders stay with the reference; everything else (KRN train / DANN target / test, SPN test) can decode-only
+        if on_device and not (cfg.model_name == 'spn' and s.get('is_train', True)):
+            from .datasets.raw import make_dataloader as make_device_dataloader
+            out.append(make_device_dataloader(cfg, device=select_device(cfg), **s))
+        else:
+            reference_modules(cfg)
+            from src.datasets.build import make_dataloader
+            out.append(make_dataloader(cfg, **s))
+    return out
 
 
 def resume(cfg, model, optimizer, device):

@@ -129,3 +129,27 @@ def test_ghiasi_param_table_matches_oracle_and_synthetic_state():
     st = pg.synthetic_state(3)
     assert set(st) == {'ghiasi', 'mean', 'cov', 'base'} and st['cov'].shape == (100, 100)
     assert all(tuple(st['ghiasi'][k].shape) == tuple(a[k]) for k in a)
+
+
+def test_make_loaders_routes_spn_training_to_the_reference_dataset(monkeypatch):
+    """--device_transforms: decode-only loaders for everything except SPN training (soft targets come from SPNDataset)."""
+    import types
+    from speedplusbaseline_b200 import cli
+    calls = []
+    fake_raw = types.ModuleType('speedplusbaseline_b200.datasets.raw')
+    fake_raw.make_dataloader = lambda cfg, device=None, **s: calls.append(('device', s)) or 'dev'
+    monkeypatch.setitem(sys.modules, 'speedplusbaseline_b200.datasets.raw', fake_raw)
+    fake_ref = types.ModuleType('src.datasets.build')
+    fake_ref.make_dataloader = lambda cfg, **s: calls.append(('reference', s)) or 'ref'
+    for name in ('src', 'src.datasets'):
+        monkeypatch.setitem(sys.modules, name, types.ModuleType(name))
+    monkeypatch.setitem(sys.modules, 'src.datasets.build', fake_ref)
+    monkeypatch.setattr(cli, 'reference_modules', lambda cfg: None)
+    monkeypatch.setattr(cli.torch.cuda, 'is_available', lambda: True)
+    train, test = dict(is_train=True, is_source=True, load_labels=True), dict(is_train=False, is_source=False, load_labels=True)
+    cfg = types.SimpleNamespace(synthetic_data=0, device_transforms=True, use_cuda=True, model_name='spn')
+    assert cli.make_loaders(cfg, [train, test]) == ['ref', 'dev']
+    cfg.model_name = 'krn'
+    assert cli.make_loaders(cfg, [train, test]) == ['dev', 'dev']
+    cfg.device_transforms = False
+    assert cli.make_loaders(cfg, [train, test]) == ['ref', 'ref']
