@@ -311,9 +311,9 @@ inline int gemm_mode() {      // 0 legacy only, 1 measured dispatch (default), 2
     if (v < 0) { const char* e = getenv("B200SP_GEMM"); v = !e ? 1 : (e[0] == 'l' ? 0 : (e[0] == 't' ? 2 : 1)); }
     return v;
 }
-// Measured on B200 (profiles/r1_e_gemm_dispatch.txt): for long-M layers with a small N x K the register-tiled
-// CUDA-core kernel (exact fp32 FFMA, streaming split-M) beats the tcgen05 pipeline, whose 128-row tiles are mostly
-// padding there and whose per-k-block hand-offs dominate.  op: 0 fwd, 1 dgrad, 2 wgrad.
+// Measured on B200 (profiles/r1_e_gemm_dispatch.txt, column "cuda-core"): for long-M layers with a small N x K this file's
+// register-tiled mma.sync kernel (64*MI x 16*NI tiles, streaming split-M) beats the tcgen05 pipeline, whose 128-row tiles are
+// mostly padding there and whose per-k-block hand-offs dominate.  op: 0 fwd, 1 dgrad, 2 wgrad.
 inline bool prefer_cuda_cores(int op, int M, int N, int K) {
     if (M < 9408) return false;
     if (op == 2) return (long long)N * K <= 24576;
