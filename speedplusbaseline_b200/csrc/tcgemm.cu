@@ -172,9 +172,17 @@ __device__ __forceinline__ void xf_load(const b200sp_vtensor& t, int ch, XfP& p)
 template <int MODE>
 __device__ __forceinline__ float4 xf_apply(float4 x, float4 x2, const XfP& p, ActP act) {
     if (MODE == XM_PLAIN) return x;
-    if (MODE == XM_BNACT)
+    if (MODE == XM_BNACT) {
+#ifdef B200SP_LEAN_TCG
+        // ReLU / ReLU6 (slope 0; hi = +inf or 6): min(max(z, 0), hi) is two instructions per value instead of the four of the
+        // branch-free generic form, and identical for finite z.  The branch is kernel-uniform.
+        if (act.slope == 0.f)
+            return make_float4(fminf(fmaxf(fmaf(x.x, p.a.x, p.b.x), 0.f), act.hi), fminf(fmaxf(fmaf(x.y, p.a.y, p.b.y), 0.f), act.hi),
+                               fminf(fmaxf(fmaf(x.z, p.a.z, p.b.z), 0.f), act.hi), fminf(fmaxf(fmaf(x.w, p.a.w, p.b.w), 0.f), act.hi));
+#endif
         return make_float4(act_fwd(fmaf(x.x, p.a.x, p.b.x), act), act_fwd(fmaf(x.y, p.a.y, p.b.y), act),
                            act_fwd(fmaf(x.z, p.a.z, p.b.z), act), act_fwd(fmaf(x.w, p.a.w, p.b.w), act));
+    }
     return make_float4(fmaf(p.a.x, x.x, fmaf(p.b.x, x2.x, p.c.x)), fmaf(p.a.y, x.y, fmaf(p.b.y, x2.y, p.c.y)),
                        fmaf(p.a.z, x.z, fmaf(p.b.z, x2.z, p.c.z)), fmaf(p.a.w, x.w, fmaf(p.b.w, x2.w, p.c.w)));
 }
