@@ -14,6 +14,8 @@
 #include "common.cuh"
 #include "tcgemm.cuh"
 
+int pwdirect_fwd(const b200sp_vtensor* x, const float* w, const float* bias, int out_act, float* y, const b200sp_bnfwd* bn,
+                 int M, int N, int K, cudaStream_t st);       // pwdirect.cu
 extern "C" int b200sp_colsum_f32(const b200sp_vtensor* dy, float* out, int M, int N, int dtype, void* stream);
 
 namespace {
@@ -337,6 +339,10 @@ inline bool use_tc(int op, int M, int N, int K) {
 extern "C" int b200sp_pw_fwd(const b200sp_vtensor* x, const float* w, const float* bias, int out_act, void* y,
                              const b200sp_bnfwd* bn, int M, int N, int K, int dtype, void* stream) {
     if (!x || x->mode == B200SP_VT_DY) return B200SP_EINVAL;
+    if (dtype == B200SP_F32) {           // round-2 candidate (B200SP_PWDIRECT=1): exact-fp32 FFMA kernel for the long-M / tiny-N*K shapes
+        const int rc = pwdirect_fwd(x, w, bias, out_act, (float*)y, bn, M, N, K, (cudaStream_t)stream);
+        if (rc != B200SP_ENOSYS) return rc;
+    }
     if (dtype == B200SP_BF16 || use_tc(0, M, N, K)) {
         TcgProblem p = {};
         p.a = *x; p.b = plain_vt(w); p.a_lay = TCG_LAY_KM; p.b_lay = TCG_LAY_KM;
