@@ -16,6 +16,8 @@
 
 int pwdirect_fwd(const b200sp_vtensor* x, const float* w, const float* bias, int out_act, float* y, const b200sp_bnfwd* bn,
                  int M, int N, int K, cudaStream_t st);       // pwdirect.cu
+int pwdirect_dgrad(const b200sp_vtensor* dy, const float* w, const float* skip, float scale_out, float* g, const b200sp_bnbwd* bn,
+                   int M, int N, int K, cudaStream_t st);     // pwdirect.cu
 extern "C" int b200sp_colsum_f32(const b200sp_vtensor* dy, float* out, int M, int N, int dtype, void* stream);
 
 namespace {
@@ -366,6 +368,10 @@ extern "C" int b200sp_pw_fwd(const b200sp_vtensor* x, const float* w, const floa
 extern "C" int b200sp_pw_dgrad(const b200sp_vtensor* dy, const float* w, const void* skip, float scale_out, void* g,
                                const b200sp_bnbwd* bn, int M, int N, int K, int dtype, void* stream) {
     if (!dy) return B200SP_EINVAL;
+    if (dtype == B200SP_F32) {           // round-2 candidate (B200SP_PWDIRECT=1)
+        const int rc = pwdirect_dgrad(dy, w, (const float*)skip, scale_out, (float*)g, bn, M, N, K, (cudaStream_t)stream);
+        if (rc != B200SP_ENOSYS) return rc;
+    }
     if (dtype == B200SP_BF16 || use_tc(1, M, N, K)) {
         TcgProblem p = {};
         p.a = *dy; p.b = plain_vt(w); p.a_lay = TCG_LAY_KM; p.b_lay = TCG_LAY_MM;
