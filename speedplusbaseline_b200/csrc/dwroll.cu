@@ -391,6 +391,314 @@ __global__ void __launch_bounds__(RNT, 3) dwr_bwd_kernel(const b200sp_vtensor dy
         for (int cc = tid; cc < gm.C; cc += RNT) bn_bwd_finalize_channel(bn, cc, gm.count);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward, second generation (round-2 candidate, selected with B200SP_DW=2; v1 above stays the default until measured).
+// Specialised for the shape every MobileNetV2 block has -- dy is a BatchNorm-backward virtual tensor (XM_DY), the conv input is
+// act(BN(y_in)) of the SAME tensor whose BatchNorm receives the gradient, activation ReLU / ReLU6, no skip gradient -- and written
+// against the source-level profile of v1 (profiles/r1_o_ncu_source_lines.txt): 773 SASS instructions per 2x2 block for ~150
+// essential FFMAs, 168 registers (12 warps/SM), and 44 compare-and-swap loops per thread for the shared-memory float atomics.
+//   * activation fixed at compile time (2 FMNMX per value instead of the 4-instruction branch-free generic form),
+//   * 32-bit element offsets, column offsets and column validity hoisted out of the row loop,
+//   * out-of-range dy taps zeroed by a 0/1 multiplier instead of per-value selects,
+//   * weight-gradient / statistic partials staged in shared memory with plain vector stores and summed by a few threads
+//     (one red.global.add.v4.f32 per 16 bytes), no shared atomics.
+template <int ACT> __device__ __forceinline__ float actf2(float z) {
+    return ACT == B200SP_ACT_RELU6 ? fminf(fmaxf(z, 0.f), 6.f) : fmaxf(z, 0.f);
+}
+template <int ACT> __device__ __forceinline__ bool actd2(float z) {            // act'(z) != 0  (open interval, like act_bwd)
+    return ACT == B200SP_ACT_RELU6 ? (z > 0.f && z < 6.f) : (z > 0.f);
+}
+__device__ __forceinline__ float4 f4scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ float4 ldf4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+struct Bwd2Shared {
+    float4 w[9][MAXCB];
+    float4 dw[RNT][9];              // per-thread weight-gradient partials, [thread][tap]: stride 144 B -> conflict-free
+    float4 s1[RNT], s2[RNT];
+};
+
+// one input pixel: z = BN pre-activation, av = conv input value, g = (dgrad) * act'(z); statistics partials
+template <int ACT>
+__device__ __forceinline__ float4 bwd2_finish(float4 dg, float4 yin, float4 z, float4& ls1, float4& ls2) {
+    dg.x = actd2<ACT>(z.x) ? dg.x : 0.f; dg.y = actd2<ACT>(z.y) ? dg.y : 0.f;
+    dg.z = actd2<ACT>(z.z) ? dg.z : 0.f; dg.w = actd2<ACT>(z.w) ? dg.w : 0.f;
+    ls1 = f4add(ls1, dg);
+    ls2 = f4fma(dg, yin, ls2);
+    return dg;
+}
+
+template <int S, int ACT>
+__global__ void __launch_bounds__(RNT, S == 2 ? 4 : 3) dwr_bwd2_kernel(const b200sp_vtensor dy, const float* __restrict__ w9c,
+                                                          float* __restrict__ g_in, float* __restrict__ dw9c,
+                                                          const b200sp_bnbwd bn, const RGeom gm) {
+    extern __shared__ __align__(16) unsigned char bwd2_smem[];
+    Bwd2Shared& sh = *reinterpret_cast<Bwd2Shared*>(bwd2_smem);
+    const int tid = threadIdx.x;
+    const int cl = tid % gm.CB, sl = tid / gm.CB;
+    const int cbase = blockIdx.y * gm.CB * 4;
+    const int c = cbase + cl * 4;
+    for (int i = tid; i < 9 * gm.CB; i += RNT) sh.w[i / gm.CB][i % gm.CB] = ldg4(w9c + (size_t)(i / gm.CB) * gm.C + cbase + (i % gm.CB) * 4);
+    __syncthreads();
+
+    const Item it = get_item(gm, sl, S == 1 ? gm.H : gm.Ho);
+    float4 ls1 = f4zero(), ls2 = f4zero();
+    float4 dwacc[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) dwacc[t] = f4zero();
+    if (it.ok) {
+        const float4 cA = ldg4(dy.p0 + c), cB = ldg4(dy.p1 + c), cC = ldg4(dy.p2 + c);      // dy = cA*g + cB*y + cC
+        const float4 sc = ldg4(bn.scale + c), shf = ldg4(bn.shift + c);
+        const float* __restrict__ gq = reinterpret_cast<const float*>(dy.x);
+        const float* __restrict__ yq = reinterpret_cast<const float*>(dy.x2);
+        const float* __restrict__ yb = reinterpret_cast<const float*>(bn.y);
+        const int C = gm.C;
+        auto dyv = [&](int off, float m) {           // transformed dy at element offset `off`, times the 0/1 validity factor
+            const float4 g = ldf4(gq + off), y = ldf4(yq + off);
+            return f4scale(f4fma(cA, g, f4fma(cB, y, cC)), m);
+        };
+        if (S == 2) {
+            // item = block column cb (input columns 2cb, 2cb+1), block rows [r_a, r_b): input rows 2a, 2a+1 receive dy(a..a+1, cb..cb+1)
+            const int cb = it.wg;
+            const bool c1 = cb + 1 < gm.Wo, w1 = 2 * cb + 1 < gm.W;
+            const float m1 = c1 ? 1.f : 0.f;
+            const int dcol = c1 ? C : 0;                                   // dy column cb+1 (clamped onto cb when outside)
+            const int drow = gm.Wo * C, xrow = gm.W * C, xcol = w1 ? C : 0;
+            int od = ((it.b * gm.Ho + it.r_a) * gm.Wo + cb) * C + c;       // dy(a, cb)
+            int ox = ((it.b * gm.H + 2 * it.r_a) * gm.W + 2 * cb) * C + c; // input (2a, 2cb)
+            float4 E00 = dyv(od, 1.f), E01 = dyv(od + dcol, m1);
+            for (int a = it.r_a; a < it.r_b; ++a) {
+                const bool r1 = a + 1 < gm.Ho, h1 = 2 * a + 1 < gm.H;
+                const int odn = od + (r1 ? drow : 0);
+                const float mr = r1 ? 1.f : 0.f;
+                // all loads of the step first
+                const float4 g10 = ldf4(gq + odn), y10 = ldf4(yq + odn), g11 = ldf4(gq + odn + dcol), y11 = ldf4(yq + odn + dcol);
+                const int oxh = ox + (h1 ? xrow : 0);
+                const float4 yi0 = ldf4(yb + ox), yi1 = ldf4(yb + ox + xcol), yi2 = ldf4(yb + oxh), yi3 = ldf4(yb + oxh + xcol);
+                const float4 E10 = f4scale(f4fma(cA, g10, f4fma(cB, y10, cC)), mr);
+                const float4 E11 = f4scale(f4fma(cA, g11, f4fma(cB, y11, cC)), mr * m1);
+                {   // (ph, pw) = (0, 0): tap 4
+                    const float4 z = f4fma(yi0, sc, shf);
+                    const float4 av = make_float4(actf2<ACT>(z.x), actf2<ACT>(z.y), actf2<ACT>(z.z), actf2<ACT>(z.w));
+                    float4 dg = f4mul(E00, sh.w[4][cl]);
+                    dwacc[4] = f4fma(av, E00, dwacc[4]);
+                    Vec4<float>::st(g_in + ox, bwd2_finish<ACT>(dg, yi0, z, ls1, ls2));
+                }
+                if (w1) {   // (0, 1): taps 5, 3
+                    const float4 z = f4fma(yi1, sc, shf);
+                    const float4 av = make_float4(actf2<ACT>(z.x), actf2<ACT>(z.y), actf2<ACT>(z.z), actf2<ACT>(z.w));
+                    float4 dg = f4mul(E00, sh.w[5][cl]); dg = f4fma(E01, sh.w[3][cl], dg);
+                    dwacc[5] = f4fma(av, E00, dwacc[5]); dwacc[3] = f4fma(av, E01, dwacc[3]);
+                    Vec4<float>::st(g_in + ox + xcol, bwd2_finish<ACT>(dg, yi1, z, ls1, ls2));
+                }
+                if (h1) {   // (1, 0): taps 7, 1
+                    const float4 z = f4fma(yi2, sc, shf);
+                    const float4 av = make_float4(actf2<ACT>(z.x), actf2<ACT>(z.y), actf2<ACT>(z.z), actf2<ACT>(z.w));
+                    float4 dg = f4mul(E00, sh.w[7][cl]); dg = f4fma(E10, sh.w[1][cl], dg);
+                    dwacc[7] = f4fma(av, E00, dwacc[7]); dwacc[1] = f4fma(av, E10, dwacc[1]);
+                    Vec4<float>::st(g_in + oxh, bwd2_finish<ACT>(dg, yi2, z, ls1, ls2));
+                }
+                if (h1 && w1) {   // (1, 1): taps 8, 6, 2, 0
+                    const float4 z = f4fma(yi3, sc, shf);
+                    const float4 av = make_float4(actf2<ACT>(z.x), actf2<ACT>(z.y), actf2<ACT>(z.z), actf2<ACT>(z.w));
+                    float4 dg = f4mul(E00, sh.w[8][cl]); dg = f4fma(E01, sh.w[6][cl], dg);
+                    dg = f4fma(E10, sh.w[2][cl], dg); dg = f4fma(E11, sh.w[0][cl], dg);
+                    dwacc[8] = f4fma(av, E00, dwacc[8]); dwacc[6] = f4fma(av, E01, dwacc[6]);
+                    dwacc[2] = f4fma(av, E10, dwacc[2]); dwacc[0] = f4fma(av, E11, dwacc[0]);
+                    Vec4<float>::st(g_in + oxh + xcol, bwd2_finish<ACT>(dg, yi3, z, ls1, ls2));
+                }
+                E00 = E10; E01 = E11;
+                od += drow; ox += 2 * xrow;
+            }
+        } else {
+            // item = input columns wi0, wi0+1, input rows [r_a, r_b); dy columns wi0-1 .. wi0+2 (NC = 4), rows hi-1 .. hi+1 rolling
+            const int wi0 = it.wg * 2;
+            const bool p1 = wi0 + 1 < gm.W;
+            int dco[4];
+            float mc[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int col = wi0 - 1 + j;
+                mc[j] = (col >= 0 && col < gm.Wo) ? 1.f : 0.f;
+                dco[j] = min(max(col, 0), gm.Wo - 1) * C;
+            }
+            const int drow = gm.Wo * C;
+            const int dbase = (it.b * gm.Ho) * gm.Wo * C + c;              // dy(b, 0, 0)
+            auto dyrow = [&](int row, float4 (&D)[4]) {
+                const float mr = (row >= 0 && row < gm.Ho) ? 1.f : 0.f;
+                const int o = dbase + min(max(row, 0), gm.Ho - 1) * drow;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) D[j] = dyv(o + dco[j], mr * mc[j]);
+            };
+            float4 D0[4], D1[4], D2[4];
+            dyrow(it.r_a - 1, D0);
+            dyrow(it.r_a, D1);
+            int ox = ((it.b * gm.H + it.r_a) * gm.W + wi0) * C + c;
+            const int xcol = p1 ? C : 0, xrow = gm.W * C;
+            for (int hi = it.r_a; hi < it.r_b; ++hi) {
+                const int rn = hi + 1;
+                const float mr = rn < gm.Ho ? 1.f : 0.f;
+                const int o = dbase + min(rn, gm.Ho - 1) * drow;
+                float4 g[4], y[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { g[j] = ldf4(gq + o + dco[j]); y[j] = ldf4(yq + o + dco[j]); }
+                const float4 yi0 = ldf4(yb + ox), yi1 = ldf4(yb + ox + xcol);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) D2[j] = f4scale(f4fma(cA, g[j], f4fma(cB, y[j], cC)), mr * mc[j]);
+#pragma unroll
+                for (int o2 = 0; o2 < 2; ++o2) {
+                    if (o2 == 0 || p1) {
+                        const float4 yi = o2 == 0 ? yi0 : yi1;
+                        const float4 z = f4fma(yi, sc, shf);
+                        const float4 av = make_float4(actf2<ACT>(z.x), actf2<ACT>(z.y), actf2<ACT>(z.z), actf2<ACT>(z.w));
+                        float4 dg = f4zero();
+                        // output (hi+dh, wi+dw) used tap (kh,kw) = (1-dh, 1-dw);  D<r>[o2+sx] holds dh = r-1, dw = sx-1
+#pragma unroll
+                        for (int sx = 0; sx < 3; ++sx) {
+                            dg = f4fma(D0[o2 + sx], sh.w[6 + (2 - sx)][cl], dg);
+                            dg = f4fma(D1[o2 + sx], sh.w[3 + (2 - sx)][cl], dg);
+                            dg = f4fma(D2[o2 + sx], sh.w[0 + (2 - sx)][cl], dg);
+                            dwacc[6 + (2 - sx)] = f4fma(av, D0[o2 + sx], dwacc[6 + (2 - sx)]);
+                            dwacc[3 + (2 - sx)] = f4fma(av, D1[o2 + sx], dwacc[3 + (2 - sx)]);
+                            dwacc[0 + (2 - sx)] = f4fma(av, D2[o2 + sx], dwacc[0 + (2 - sx)]);
+                        }
+                        Vec4<float>::st(g_in + ox + (o2 ? xcol : 0), bwd2_finish<ACT>(dg, yi, z, ls1, ls2));
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { D0[j] = D1[j]; D1[j] = D2[j]; }
+                ox += xrow;
+            }
+        }
+        // s2 = sum g*xhat = rstd * (sum g*y - mean * sum g)
+        const float4 mu = ldg4(bn.mean + c), rs = ldg4(bn.rstd + c);
+        ls2 = make_float4(rs.x * (ls2.x - mu.x * ls1.x), rs.y * (ls2.y - mu.y * ls1.y), rs.z * (ls2.z - mu.z * ls1.z), rs.w * (ls2.w - mu.w * ls1.w));
+    }
+    // ---- CTA-level reduction of the partials: plain vector stores, then (tap, channel quad) owners sum over the items ----
+#pragma unroll
+    for (int t = 0; t < 9; ++t) sh.dw[tid][t] = dwacc[t];
+    sh.s1[tid] = ls1;
+    sh.s2[tid] = ls2;
+    __syncthreads();
+    const int nsl = RNT / gm.CB;                     // items per CTA (threads beyond nsl*CB hold zeros and are not read)
+    for (int i = tid; i < 9 * gm.CB; i += RNT) {
+        const int t = i / gm.CB, q = i - t * gm.CB;
+        float4 a = f4zero();
+        for (int s2i = 0; s2i < nsl; ++s2i) a = f4add(a, sh.dw[s2i * gm.CB + q][t]);
+        float* dst = dw9c + (size_t)t * gm.C + cbase + q * 4;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+    }
+    if (tid < gm.CB * 4) {
+        const int q = tid >> 2, k = tid & 3;
+        float a = 0.f, b = 0.f;
+        for (int s2i = 0; s2i < nsl; ++s2i) {
+            a += reinterpret_cast<const float*>(&sh.s1[s2i * gm.CB + q])[k];
+            b += reinterpret_cast<const float*>(&sh.s2[s2i * gm.CB + q])[k];
+        }
+        atomicAdd(bn.s1 + cbase + tid, (double)a);
+        atomicAdd(bn.s2 + cbase + tid, (double)b);
+    }
+    if (grid_last_cta(bn.ticket, gridDim.x * gridDim.y))
+        for (int cc = tid; cc < gm.C; cc += RNT) bn_bwd_finalize_channel(bn, cc, gm.count);
+}
+
+// Forward, second generation (same recipe as dwr_bwd2_kernel; B200SP_DW=2).  Input = act(BN(y_prev)) with the activation fixed
+// at compile time, zero padding applied as a 0/1 multiplier, 32-bit offsets with the column part hoisted out of the row loop,
+// BatchNorm statistic partials staged in shared memory (no shared atomics).  v1: 539 / 520 SASS instructions per row step
+// (stride 1 / 2) for 144 / 72 essential FFMAs.
+struct Fwd2Shared {
+    float4 w[9][MAXCB];
+    float4 s1[RNT], s2[RNT];
+};
+
+template <int S, int ACT>
+__global__ void __launch_bounds__(RNT, S == 2 ? 4 : 3) dwr_fwd2_kernel(const b200sp_vtensor x, const float* __restrict__ w9c,
+                                                                       float* __restrict__ y, const b200sp_bnfwd bn, const RGeom gm) {
+    constexpr int OW = S == 1 ? 4 : 2;
+    constexpr int NC = (OW - 1) * S + 3;
+    __shared__ Fwd2Shared sh;
+    const int tid = threadIdx.x;
+    const int cl = tid % gm.CB, sl = tid / gm.CB;
+    const int cbase = blockIdx.y * gm.CB * 4;
+    const int c = cbase + cl * 4;
+    for (int i = tid; i < 9 * gm.CB; i += RNT) sh.w[i / gm.CB][i % gm.CB] = ldg4(w9c + (size_t)(i / gm.CB) * gm.C + cbase + (i % gm.CB) * 4);
+    __syncthreads();
+
+    const Item it = get_item(gm, sl, gm.Ho);
+    float4 lsum = f4zero(), lsq = f4zero();
+    if (it.ok) {
+        const float4 sc = ldg4(x.p0 + c), shf = ldg4(x.p1 + c);
+        const float* __restrict__ xq = reinterpret_cast<const float*>(x.x);
+        const int C = gm.C;
+        const int wo0 = it.wg * OW, wi0 = wo0 * S - 1;
+        int xco[NC];
+        float mc[NC];
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            const int col = wi0 + j;
+            mc[j] = (col >= 0 && col < gm.W) ? 1.f : 0.f;
+            xco[j] = min(max(col, 0), gm.W - 1) * C;
+        }
+        const int xrow = gm.W * C;
+        const int xbase = it.b * gm.H * xrow + c;
+        auto loadrow = [&](int row, float4 (&r)[NC]) {
+            const float mr = (row >= 0 && row < gm.H) ? 1.f : 0.f;
+            const int o = xbase + min(max(row, 0), gm.H - 1) * xrow;
+            float4 raw[NC];
+#pragma unroll
+            for (int j = 0; j < NC; ++j) raw[j] = ldf4(xq + o + xco[j]);
+#pragma unroll
+            for (int j = 0; j < NC; ++j) {
+                const float4 z = f4fma(raw[j], sc, shf);
+                r[j] = f4scale(make_float4(actf2<ACT>(z.x), actf2<ACT>(z.y), actf2<ACT>(z.z), actf2<ACT>(z.w)), mr * mc[j]);
+            }
+        };
+        float4 r0[NC], r1[NC], r2[NC];
+        if (S == 1) { loadrow(it.r_a - 1, r0); loadrow(it.r_a, r1); }
+        else        { loadrow(2 * it.r_a - 1, r0); }
+        int oy = ((it.b * gm.Ho + it.r_a) * gm.Wo + wo0) * C + c;
+        const int yrow = gm.Wo * C;
+        for (int ho = it.r_a; ho < it.r_b; ++ho) {
+            if (S == 1) { loadrow(ho + 1, r2); }
+            else        { loadrow(2 * ho, r1); loadrow(2 * ho + 1, r2); }
+#pragma unroll
+            for (int o = 0; o < OW; ++o) {
+                float4 acc = f4mul(r0[o * S], sh.w[0][cl]);
+                acc = f4fma(r0[o * S + 1], sh.w[1][cl], acc); acc = f4fma(r0[o * S + 2], sh.w[2][cl], acc);
+                acc = f4fma(r1[o * S], sh.w[3][cl], acc); acc = f4fma(r1[o * S + 1], sh.w[4][cl], acc); acc = f4fma(r1[o * S + 2], sh.w[5][cl], acc);
+                acc = f4fma(r2[o * S], sh.w[6][cl], acc); acc = f4fma(r2[o * S + 1], sh.w[7][cl], acc); acc = f4fma(r2[o * S + 2], sh.w[8][cl], acc);
+                if (wo0 + o < gm.Wo) {
+                    Vec4<float>::st(y + oy + o * C, acc);
+                    lsum = f4add(lsum, acc);
+                    lsq = f4fma(acc, acc, lsq);
+                }
+            }
+            if (S == 1) {
+#pragma unroll
+                for (int j = 0; j < NC; ++j) { r0[j] = r1[j]; r1[j] = r2[j]; }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NC; ++j) r0[j] = r2[j];
+            }
+            oy += yrow;
+        }
+    }
+    sh.s1[tid] = lsum;
+    sh.s2[tid] = lsq;
+    __syncthreads();
+    if (tid < gm.CB * 4) {
+        const int nsl = RNT / gm.CB, q = tid >> 2, k = tid & 3;
+        float a = 0.f, b = 0.f;
+        for (int s2i = 0; s2i < nsl; ++s2i) {
+            a += reinterpret_cast<const float*>(&sh.s1[s2i * gm.CB + q])[k];
+            b += reinterpret_cast<const float*>(&sh.s2[s2i * gm.CB + q])[k];
+        }
+        atomicAdd(bn.sum + cbase + tid, (double)a);
+        atomicAdd(bn.sumsq + cbase + tid, (double)b);
+    }
+    if (grid_last_cta(bn.ticket, gridDim.x * gridDim.y))
+        for (int cc = tid; cc < gm.C; cc += RNT) bn_fwd_finalize_channel(bn, cc, gm.count);
+}
+
 // rows: number of rolled rows; cols: number of column groups; count: BatchNorm population
 int roll_geom(RGeom& gm, dim3& grid, int B, int H, int W, int C, int stride, int rows, int ncolgroups, double count) {
     if (C % 4 || (stride != 1 && stride != 2)) return B200SP_EINVAL;
@@ -422,6 +730,12 @@ inline bool use_roll() {
     return v == 1;
 }
 
+inline bool use_bwd2() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("B200SP_DW"); v = (e && e[0] == '2') ? 1 : 0; }
+    return v == 1;
+}
+
 template <typename T>
 int launch_fwd(const b200sp_vtensor* x, const float* w9c, void* y, const b200sp_bnfwd* bn, int B, int H, int W, int C, int stride, cudaStream_t st) {
     RGeom gm; dim3 grid;
@@ -431,6 +745,19 @@ int launch_fwd(const b200sp_vtensor* x, const float* w9c, void* y, const b200sp_
     b200sp_bnfwd b = {};
     if (bn) b = *bn;
     const bool plain = x->mode == B200SP_VT_PLAIN;
+    if (use_bwd2() && sizeof(T) == 4 && bn && x->mode == B200SP_VT_BNACT && (x->act == B200SP_ACT_RELU6 || x->act == B200SP_ACT_RELU) &&
+        (long long)B * H * W * C < (1ll << 31)) {
+        const bool r6 = x->act == B200SP_ACT_RELU6;
+        if (stride == 1) {
+            if (r6) dwr_fwd2_kernel<1, B200SP_ACT_RELU6><<<grid, RNT, 0, st>>>(*x, w9c, (float*)y, b, gm);
+            else    dwr_fwd2_kernel<1, B200SP_ACT_RELU><<<grid, RNT, 0, st>>>(*x, w9c, (float*)y, b, gm);
+        } else {
+            if (r6) dwr_fwd2_kernel<2, B200SP_ACT_RELU6><<<grid, RNT, 0, st>>>(*x, w9c, (float*)y, b, gm);
+            else    dwr_fwd2_kernel<2, B200SP_ACT_RELU><<<grid, RNT, 0, st>>>(*x, w9c, (float*)y, b, gm);
+        }
+        B200SP_COUNT_LAUNCH();
+        B200SP_RETURN_LAST();
+    }
     if (stride == 1) {
         if (plain) dwr_fwd_kernel<T, 1, XM_PLAIN><<<grid, RNT, 0, st>>>(*x, w9c, (T*)y, b, bn != nullptr, gm);
         else       dwr_fwd_kernel<T, 1, XM_BNACT><<<grid, RNT, 0, st>>>(*x, w9c, (T*)y, b, bn != nullptr, gm);
@@ -452,6 +779,30 @@ int launch_bwd(const b200sp_vtensor* dy, const b200sp_vtensor* x, const float* w
     if (int rc = roll_geom(gm, grid, B, H, W, C, stride, rows, ncg, (double)B * H * W)) return rc;
     b200sp_bnbwd b = {};
     if (bn) b = *bn;
+    if (use_bwd2() && sizeof(T) == 4 && bn && dy->mode == B200SP_VT_DY && x->mode == B200SP_VT_BNACT && x->x == bn->y && !skip && g_in &&
+        bn->scale && bn->s1 && x->act == bn->act && (bn->act == B200SP_ACT_RELU6 || bn->act == B200SP_ACT_RELU) &&
+        x->p0 == bn->scale && x->p1 == bn->shift &&
+        (long long)B * H * W * C < (1ll << 31) && (long long)B * Ho * Wo * C < (1ll << 31)) {
+        static bool attr_set = false;
+        const int smem = (int)sizeof(Bwd2Shared);
+        if (!attr_set) {
+            cudaFuncSetAttribute(dwr_bwd2_kernel<1, B200SP_ACT_RELU6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cudaFuncSetAttribute(dwr_bwd2_kernel<2, B200SP_ACT_RELU6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cudaFuncSetAttribute(dwr_bwd2_kernel<1, B200SP_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cudaFuncSetAttribute(dwr_bwd2_kernel<2, B200SP_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            attr_set = true;
+        }
+        const bool r6 = bn->act == B200SP_ACT_RELU6;
+        if (stride == 1) {
+            if (r6) dwr_bwd2_kernel<1, B200SP_ACT_RELU6><<<grid, RNT, smem, st>>>(*dy, w9c, (float*)g_in, dw9c, b, gm);
+            else    dwr_bwd2_kernel<1, B200SP_ACT_RELU><<<grid, RNT, smem, st>>>(*dy, w9c, (float*)g_in, dw9c, b, gm);
+        } else {
+            if (r6) dwr_bwd2_kernel<2, B200SP_ACT_RELU6><<<grid, RNT, smem, st>>>(*dy, w9c, (float*)g_in, dw9c, b, gm);
+            else    dwr_bwd2_kernel<2, B200SP_ACT_RELU><<<grid, RNT, smem, st>>>(*dy, w9c, (float*)g_in, dw9c, b, gm);
+        }
+        B200SP_COUNT_LAUNCH();
+        B200SP_RETURN_LAST();
+    }
 #define DWR_BWD(S_, DM_, XM_) dwr_bwd_kernel<T, S_, DM_, XM_><<<grid, RNT, 0, st>>>(*dy, *x, w9c, (const T*)skip, (T*)g_in, dw9c, b, bn != nullptr, gm)
     const bool ddy = dy->mode == B200SP_VT_DY, xbn = x->mode == B200SP_VT_BNACT;
     if (dy->mode == B200SP_VT_BNACT) return B200SP_EINVAL;

@@ -14,6 +14,10 @@
 #include "common.cuh"
 #include "tcgemm.cuh"
 
+int pwdirect_fwd(const b200sp_vtensor* x, const float* w, const float* bias, int out_act, float* y, const b200sp_bnfwd* bn,
+                 int M, int N, int K, cudaStream_t st);       // pwdirect.cu
+int pwdirect_dgrad(const b200sp_vtensor* dy, const float* w, const float* skip, float scale_out, float* g, const b200sp_bnbwd* bn,
+                   int M, int N, int K, cudaStream_t st);     // pwdirect.cu
 extern "C" int b200sp_colsum_f32(const b200sp_vtensor* dy, float* out, int M, int N, int dtype, void* stream);
 
 namespace {
@@ -41,7 +45,11 @@ struct GemmArgs {
 };
 
 __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+#ifdef B200SP_LEAN_TCG
+    hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;      // == cvt.rna.tf32.f32 for finite v, 2 instead of 4 SASS instructions
+#else
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
+#endif
     lo = __float_as_uint(v - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
@@ -333,6 +341,10 @@ inline bool use_tc(int op, int M, int N, int K) {
 extern "C" int b200sp_pw_fwd(const b200sp_vtensor* x, const float* w, const float* bias, int out_act, void* y,
                              const b200sp_bnfwd* bn, int M, int N, int K, int dtype, void* stream) {
     if (!x || x->mode == B200SP_VT_DY) return B200SP_EINVAL;
+    if (dtype == B200SP_F32) {           // round-2 candidate (B200SP_PWDIRECT=1): exact-fp32 FFMA kernel for the long-M / tiny-N*K shapes
+        const int rc = pwdirect_fwd(x, w, bias, out_act, (float*)y, bn, M, N, K, (cudaStream_t)stream);
+        if (rc != B200SP_ENOSYS) return rc;
+    }
     if (dtype == B200SP_BF16 || use_tc(0, M, N, K)) {
         TcgProblem p = {};
         p.a = *x; p.b = plain_vt(w); p.a_lay = TCG_LAY_KM; p.b_lay = TCG_LAY_KM;
@@ -356,6 +368,10 @@ extern "C" int b200sp_pw_fwd(const b200sp_vtensor* x, const float* w, const floa
 extern "C" int b200sp_pw_dgrad(const b200sp_vtensor* dy, const float* w, const void* skip, float scale_out, void* g,
                                const b200sp_bnbwd* bn, int M, int N, int K, int dtype, void* stream) {
     if (!dy) return B200SP_EINVAL;
+    if (dtype == B200SP_F32) {           // round-2 candidate (B200SP_PWDIRECT=1)
+        const int rc = pwdirect_dgrad(dy, w, (const float*)skip, scale_out, (float*)g, bn, M, N, K, (cudaStream_t)stream);
+        if (rc != B200SP_ENOSYS) return rc;
+    }
     if (dtype == B200SP_BF16 || use_tc(1, M, N, K)) {
         TcgProblem p = {};
         p.a = *dy; p.b = plain_vt(w); p.a_lay = TCG_LAY_KM; p.b_lay = TCG_LAY_MM;

@@ -73,6 +73,7 @@ struct TcgArgs {
     b200sp_bnbwd bnb;
     double count;
     int wait_mode;
+    uint32_t epi_sleep;              // epilogue back-off in ns (B200SP_LEAN_TCG builds only)
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
@@ -103,10 +104,10 @@ __device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t parity, 
 
 // long waits (the epilogue waits for a whole main loop): back off so the spin does not steal issue
 // slots from the producer warps sharing the scheduler
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns = 256) {
     uint32_t spins = 0;
     while (!tc::mbar_try_wait(bar, parity)) {
-        __nanosleep(256);
+        __nanosleep(ns);
         if (++spins > (1u << 24)) __trap();
     }
 }
@@ -172,9 +173,17 @@ __device__ __forceinline__ void xf_load(const b200sp_vtensor& t, int ch, XfP& p)
 template <int MODE>
 __device__ __forceinline__ float4 xf_apply(float4 x, float4 x2, const XfP& p, ActP act) {
     if (MODE == XM_PLAIN) return x;
-    if (MODE == XM_BNACT)
+    if (MODE == XM_BNACT) {
+#ifdef B200SP_LEAN_TCG
+        // ReLU / ReLU6 (slope 0; hi = +inf or 6): min(max(z, 0), hi) is two instructions per value instead of the four of the
+        // branch-free generic form, and identical for finite z.  The branch is kernel-uniform.
+        if (act.slope == 0.f)
+            return make_float4(fminf(fmaxf(fmaf(x.x, p.a.x, p.b.x), 0.f), act.hi), fminf(fmaxf(fmaf(x.y, p.a.y, p.b.y), 0.f), act.hi),
+                               fminf(fmaxf(fmaf(x.z, p.a.z, p.b.z), 0.f), act.hi), fminf(fmaxf(fmaf(x.w, p.a.w, p.b.w), 0.f), act.hi));
+#endif
         return make_float4(act_fwd(fmaf(x.x, p.a.x, p.b.x), act), act_fwd(fmaf(x.y, p.a.y, p.b.y), act),
                            act_fwd(fmaf(x.z, p.a.z, p.b.z), act), act_fwd(fmaf(x.w, p.a.w, p.b.w), act));
+    }
     return make_float4(fmaf(p.a.x, x.x, fmaf(p.b.x, x2.x, p.c.x)), fmaf(p.a.y, x.y, fmaf(p.b.y, x2.y, p.c.y)),
                        fmaf(p.a.z, x.z, fmaf(p.b.z, x2.z, p.c.z)), fmaf(p.a.w, x.w, fmaf(p.b.w, x2.w, p.c.w)));
 }
@@ -578,7 +587,11 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
             const Item w = get_item(g, it);
             if (do_stats && cur_q0 >= 0 && cur_q0 != w.q0) flush(cur_q0);
             cur_q0 = w.q0;
+#ifdef B200SP_LEAN_TCG
+            mbar_wait_sleep(&tfull[acc], tpar, g.epi_sleep);      // env B200SP_TCG_EPI_SLEEP: the 256 ns back-off returns after ~40 ns (r1j profile)
+#else
             mbar_wait_sleep(&tfull[acc], tpar);
+#endif
             tc::tc_fence_after();
             const uint32_t t_row = tmem_base + acc * g.acc_cols + ((uint32_t)(lq * 32) << 16);
             const bool split_acc = g.acc_cols > g.BN;
@@ -883,6 +896,9 @@ int tcgemm_launch(const TcgProblem& p, cudaStream_t st) {
         static int wm = -1;
         if (wm < 0) { const char* e = getenv("B200SP_TCG_WAIT"); wm = e ? atoi(e) : 0; }
         a.wait_mode = wm;
+        static int es = -1;
+        if (es < 0) { const char* e = getenv("B200SP_TCG_EPI_SLEEP"); es = e ? atoi(e) : 256; }
+        a.epi_sleep = (uint32_t)es;
     }
     if (p.dtype == B200SP_F32) return launch_T<float>(a, p, st);
     if (p.dtype == B200SP_BF16) return launch_T<bf16>(a, p, st);
