@@ -31,6 +31,7 @@ class EngineModule(nn.Module):
 
     def _register_store(self, store, key_order):
         self._store, self._key_order = store, key_order
+        store.key_order = list(key_order)       # reference parameters() order for the optimizer checkpoint (optim.py)
         self._plist = nn.ParameterList()
         for k, e in store.entries.items():
             p = nn.Parameter(store.params[e.off:e.off + e.numel])

@@ -81,30 +81,99 @@ class FusedAdamW(torch.optim.Optimizer):
         else:
             L.call('b200sp_optim_step', self.KIND, st.params.data_ptr(), st.grads.data_ptr(), self.exp_avg.data_ptr(),
                    L.ptr(self.exp_avg_sq), lowp, st.n, hp, sp)
-        self._step_host += 1
 
     def zero_grad(self, set_to_none=True):
         self.store.grads.zero_()
 
+    def _device_hp(self):
+        return L.AdamWHp.from_buffer_copy(self._hp.cpu().numpy().tobytes())
+
     def last_grad_norm(self):
-        cur = self._hp.cpu().numpy().tobytes()
-        h = L.AdamWHp.from_buffer_copy(cur)
-        return h.last_norm
+        return self._device_hp().last_norm
+
+    def device_step(self):
+        """Number of optimizer steps taken, read from the device-resident counter: CUDA-graph replays advance it without
+        Python's step() running, so the host copy is only the value last pushed."""
+        self._step_host = int(self._device_hp().step)
+        return self._step_host
+
+    # ---- checkpoint format: torch.optim's own (reference utils.py:109-135 stores optimizer.state_dict()) ------------
+    # {'state': {i: {'step', <per-parameter moment tensors in the REFERENCE shape>}}, 'param_groups': [{..., 'params': [0..n-1]}]}
+    # where i enumerates the reference module's parameters() (= its state_dict order without buffers), so a
+    # checkpoint.pth.tar written by the reference (or by this repo's --no_cuda path) resumes here and vice versa.
+    _STATE_NAMES = {L.OPT_ADAMW: ('exp_avg', 'exp_avg_sq'), L.OPT_ADAM: ('exp_avg', 'exp_avg_sq'),
+                    L.OPT_SGD: ('momentum_buffer', None), L.OPT_RMSPROP: ('square_avg', None)}
+
+    def _ref_params(self):
+        """[(flat slice, kind, reference shape)] in the reference's parameters() order."""
+        st = self.store
+        rk = st.ref_keys()
+        order = getattr(st, 'key_order', None) or list(rk)
+        out = []
+        for k in order:
+            r = rk[k]
+            if r[0] == 'w':
+                e = r[1]
+                out.append((slice(e.off, e.off + e.numel), e.kind, e.ref_shape))
+            elif r[2] in ('weight', 'bias'):
+                g, b, _, _ = st.bn_slices(r[1])
+                out.append((g if r[2] == 'weight' else b, 'plain', (st.bns[r[1]][1],)))
+        return out
 
     def state_dict(self):
-        return {'state': {'step': self._step_host, 'exp_avg': self.exp_avg.clone(),
-                          'exp_avg_sq': None if self.exp_avg_sq is None else self.exp_avg_sq.clone()},
-                'param_groups': [{k: v for k, v in g.items() if k != 'params'} for g in self.param_groups],
-                'layout': 'b200sp-flat'}
+        from .params import from_native
+        step = self.device_step()
+        n1, n2 = self._STATE_NAMES[self.KIND]
+        ref = self._ref_params()
+        state = {}
+        has_state = step > 0 and not (self.KIND == L.OPT_SGD and self.param_groups[0].get('momentum', 0) == 0)
+        if has_state:
+            for i, (sl, kind, shp) in enumerate(ref):
+                d = {}
+                if self.KIND != L.OPT_SGD:
+                    d['step'] = torch.tensor(float(step))
+                d[n1] = from_native(kind, self.exp_avg[sl], shp)
+                if n2 is not None:
+                    d[n2] = from_native(kind, self.exp_avg_sq[sl], shp)
+                state[i] = d
+        groups = []
+        for g in self.param_groups[:1]:
+            gg = {k: v for k, v in g.items() if k != 'params'}
+            gg['params'] = list(range(len(ref)))
+            groups.append(gg)
+        return {'state': state, 'param_groups': groups}
 
     def load_state_dict(self, sd):
+        from .params import to_native
         s = sd['state']
-        self.exp_avg.copy_(s['exp_avg'])
-        if self.exp_avg_sq is not None:
-            self.exp_avg_sq.copy_(s['exp_avg_sq'])
-        self._step_host = int(s['step'])
+        if sd.get('layout') == 'b200sp-flat':              # round-1 private layout: still readable
+            self.exp_avg.copy_(s['exp_avg'])
+            if self.exp_avg_sq is not None:
+                self.exp_avg_sq.copy_(s['exp_avg_sq'])
+            self._step_host = int(s['step'])
+        else:
+            n1, n2 = self._STATE_NAMES[self.KIND]
+            ref = self._ref_params()
+            if len(s) not in (0, len(ref)):
+                raise ValueError('optimizer state has %d parameters, the model has %d' % (len(s), len(ref)))
+            self.exp_avg.zero_()
+            if self.exp_avg_sq is not None:
+                self.exp_avg_sq.zero_()
+            step = 0
+            for i, (sl, kind, shp) in enumerate(ref):
+                d = s.get(i, s.get(str(i)))
+                if d is None:
+                    continue
+                if tuple(d[n1].shape) != tuple(shp):
+                    raise ValueError('optimizer state %d: shape %s, expected %s' % (i, tuple(d[n1].shape), tuple(shp)))
+                self.exp_avg[sl].copy_(to_native(kind, d[n1].to(torch.float32)).reshape(-1))
+                if n2 is not None:
+                    self.exp_avg_sq[sl].copy_(to_native(kind, d[n2].to(torch.float32)).reshape(-1))
+                if 'step' in d:
+                    step = max(step, int(float(d['step'])))
+            self._step_host = step
         for g, gs in zip(self.param_groups, sd['param_groups']):
-            g.update(gs)
+            g.update({k: v for k, v in gs.items() if k != 'params'})
         self._push(force=True)
 
 
