@@ -10,7 +10,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, 'csrc')
 SUFFIX = os.environ.get('B200SP_LIB_SUFFIX', '')       # experiment builds (e.g. _lean with B200SP_NVCC_EXTRA) live beside the default library
 LIB = os.path.join(PKG, 'libb200sp%s.so' % SUFFIX)
-NVCC_FLAGS = (os.environ.get('B200SP_NVCC_EXTRA', '').split()) + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+NVCC_FLAGS = (os.environ.get('B200SP_NVCC_EXTRA', '').split()) + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-DB200SP_LEAN_TCG',
               '-Xcompiler', '-fPIC', '-I' + os.path.join(ROOT, 'include'), '-I' + CSRC]
 
 

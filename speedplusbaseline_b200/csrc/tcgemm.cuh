@@ -31,3 +31,6 @@ struct TcgProblem {
 // returns 0 on success, B200SP_ENOSYS when the shape is outside what the tensor-core path supports
 // (the caller then uses the CUDA-core/mma.sync fallback kernel), or a cudaError_t.
 int tcgemm_launch(const TcgProblem& p, cudaStream_t st);
+
+// second-generation kernel (tcgemm2.cu): raw operands staged by TMA, lean smem->smem converters; same contract.
+int tcgemm2_launch(const TcgProblem& p, cudaStream_t st);

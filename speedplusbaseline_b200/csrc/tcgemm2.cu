@@ -1,0 +1,790 @@
+// tcgemm2.cu -- second-generation tcgen05 GEMM for the 1x1-convolution family (fp32 storage, 3xTF32 math).
+// Same problem interface (TcgProblem), MMA issue loop and epilogue as tcgemm.cu; what changed is the OPERAND PATH,
+// which bounded the first-generation kernel (475-657 SASS instructions per producer thread
+// and k-block, most of them cp.async issue / address / validity arithmetic):
+//
+//   TMA warp (1 thread)   : cp.async.bulk.tensor boxes of the RAW fp32 operands (A [, the second tensor of a folded
+//                           BatchNorm-backward operand] [, B]) into an n_raw-deep shared-memory ring; out-of-range rows /
+//                           columns are zero-filled by the TMA unit, so the kernel carries no validity masks and no global
+//                           address arithmetic at all.  Box layouts: K-major operand = {32 floats, rows} (dense rows of 128 B);
+//                           MN-major operand = one {32 floats, 32 reduction rows} box per 128-byte atom.
+//   converters (16 warps) : wait for a raw stage, ld.shared one 16-byte piece, apply the virtual-tensor transform
+//                           (BN affine + activation | dy = cA*g + cB*y + cC), split fp32 -> (tf32 hi, lo) and st.shared into
+//                           the 128B-swizzled UMMA operand tiles; piece <-> thread mapping is fixed, so the loop is
+//                           lds -> ~30 ALU -> 2 sts per piece.
+//   MMA warp / epilogue   : as in tcgemm.cu (3 tcgen05.mma kind::tf32 per k-step, correction products in their own TMEM
+//                           accumulator; tcgen05.ld -> smem transpose -> coalesced global phase with the BatchNorm reductions).
+//
+// Small weight operands (one N tile, <= 64 KB as hi+lo tiles) are streamed through the same raw ring ONCE per CTA before
+// the first A tile and stay resident.  Covers the KRN combinations: FWD (A K-major, B K-major), DGRAD (A K-major,
+// B MN-major), WGRAD (A, B MN-major; split-K, fp32 red.add).  Anything else returns B200SP_ENOSYS and the caller
+// falls back to tcgemm.cu.
+#include <cuda_bf16.h>
+#include <stdlib.h>
+#include "tcgemm.cuh"
+#include "tc_common.cuh"
+#include "tma.cuh"
+
+#define TL(row, idx) do {} while (0)
+
+namespace {
+
+constexpr int EPI_T = 256, MMA_T = 32, TMA_T = 32, PROD_T = 512;
+constexpr int APT = 1024 / PROD_T;              // 16-byte pieces of a 128-row x 128-byte tile per converter thread
+constexpr int EPI_W = EPI_T / 32;
+constexpr int EPI_SETS = EPI_W / 4;
+constexpr int MMA_WARP = EPI_W;
+constexpr int TMA_WARP = EPI_W + 1;
+constexpr int PROD_TID0 = EPI_T + MMA_T + TMA_T;
+constexpr int NT = EPI_T + MMA_T + TMA_T + PROD_T;     // 832 threads
+constexpr int BM = 128;
+constexpr int STG_LD = 36;
+constexpr int MAX_OP = 4, MAX_RAW = 6;
+
+struct ETf { static constexpr int ES = 4, KE = 32, EPV = 4, NM = 2; static constexpr bool TF32 = true; };
+
+struct alignas(64) Tcg2Args {
+    CUtensorMap mapA, mapA2, mapB;
+    b200sp_vtensor a, b;
+    int P, Q, R, lda, ldb, ldo;
+    int BN, numPt, numQt, splits, kb_per_split, nkb;
+    int n_op, n_raw;
+    int b_res;
+    int ac_last, nks_last;
+    int b_atoms;                     // MN-major B: 128-byte atoms per tile
+    uint32_t a_tx, b_tx;             // TMA bytes per k-block of one A tensor / of B
+    uint32_t off_bres;
+    uint32_t a_op_bytes, b_op_bytes;
+    uint32_t op_stage_bytes, raw_stage_bytes;
+    uint32_t off_raw, off_stg, off_stat, off_bar;
+    uint32_t tmem_cols;
+    int nacc, acc_cols, split_epi;
+    void* out;
+    const float* bias;
+    int out_act, has_bnf;
+    b200sp_bnfwd bnf;
+    const void* skip;
+    float scale_out;
+    int has_bnb;
+    b200sp_bnbwd bnb;
+    double count;
+    int wait_mode;
+    uint32_t epi_sleep;
+};
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_T) : "memory"); }
+
+// bounded waits: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t parity, int mode = 0) {
+    uint32_t spins = 0;
+    while (!tc::mbar_try_wait_hint(bar, parity, 20000u)) {
+        if (++spins > (1u << 20)) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns = 256) {
+    uint32_t spins = 0;
+    while (!tc::mbar_try_wait_hint(bar, parity, 100000u)) {      // hardware-suspended; the back-off only matters if the hint expires early
+        __nanosleep(ns);
+        if (++spins > (1u << 22)) __trap();
+    }
+}
+
+struct Item { int p0, q0, kb0, kb1; };
+__device__ __forceinline__ Item get_item(const Tcg2Args& g, int it) {
+    Item w;
+    const int qt = it % g.numQt;
+    const int t2 = it / g.numQt;
+    const int pt = t2 % g.numPt, sp = t2 / g.numPt;
+    w.p0 = pt * BM;
+    w.q0 = qt * g.BN;
+    w.kb0 = sp * g.kb_per_split;
+    w.kb1 = min(g.nkb, w.kb0 + g.kb_per_split);
+    return w;
+}
+struct KIter {
+    int it, total, stride;
+    Item w;
+    int kb;
+    __device__ __forceinline__ void init(const Tcg2Args& g, int first, int total_, int stride_) {
+        it = first; total = total_; stride = stride_;
+        if (it < total) { w = get_item(g, it); kb = w.kb0; }
+    }
+    __device__ __forceinline__ bool valid() const { return it < total; }
+    __device__ __forceinline__ void next(const Tcg2Args& g) {
+        if (++kb >= w.kb1) {
+            it += stride;
+            if (it < total) { w = get_item(g, it); kb = w.kb0; }
+        }
+    }
+};
+
+__device__ __forceinline__ float4 lds4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts4(uint32_t a, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// ---- per-channel transform of a virtual tensor, mode fixed at compile time --------------------------
+enum { XM_PLAIN = 0, XM_BNACT = 1, XM_DY = 2 };
+struct XfP { float4 a, b, c; };
+template <int MODE>
+__device__ __forceinline__ void xf_load(const b200sp_vtensor& t, int ch, XfP& p) {
+    if (MODE != XM_PLAIN) { p.a = ldg4(t.p0 + ch); p.b = ldg4(t.p1 + ch); }
+    if (MODE == XM_DY) p.c = ldg4(t.p2 + ch);
+}
+template <int MODE>
+__device__ __forceinline__ float4 xf_apply(float4 x, float4 x2, const XfP& p, ActP act) {
+    if (MODE == XM_PLAIN) return x;
+    if (MODE == XM_BNACT) {
+        if (act.slope == 0.f)        // ReLU / ReLU6: kernel-uniform branch, two instructions per value after the FMA
+            return make_float4(fminf(fmaxf(fmaf(x.x, p.a.x, p.b.x), 0.f), act.hi), fminf(fmaxf(fmaf(x.y, p.a.y, p.b.y), 0.f), act.hi),
+                               fminf(fmaxf(fmaf(x.z, p.a.z, p.b.z), 0.f), act.hi), fminf(fmaxf(fmaf(x.w, p.a.w, p.b.w), 0.f), act.hi));
+        return make_float4(act_fwd(fmaf(x.x, p.a.x, p.b.x), act), act_fwd(fmaf(x.y, p.a.y, p.b.y), act),
+                           act_fwd(fmaf(x.z, p.a.z, p.b.z), act), act_fwd(fmaf(x.w, p.a.w, p.b.w), act));
+    }
+    return make_float4(fmaf(p.a.x, x.x, fmaf(p.b.x, x2.x, p.c.x)), fmaf(p.a.y, x.y, fmaf(p.b.y, x2.y, p.c.y)),
+                       fmaf(p.a.z, x.z, fmaf(p.b.z, x2.z, p.c.z)), fmaf(p.a.w, x.w, fmaf(p.b.w, x2.w, p.c.w)));
+}
+// fp32 -> (tf32 hi, lo), both rounded to nearest: bit-identical to cvt.rna.tf32.f32 for finite inputs (tc_common.cuh), 5 instructions
+__device__ __forceinline__ void split1(float v, float& hi, float& lo) {
+    const uint32_t h = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
+    hi = __uint_as_float(h);
+    lo = __uint_as_float((__float_as_uint(v - hi) + 0x1000u) & 0xffffe000u);
+}
+__device__ __forceinline__ void split_store(float4 v, uint32_t dst_hi, uint32_t dst_lo) {
+    float4 h, l;
+    split1(v.x, h.x, l.x); split1(v.y, h.y, l.y); split1(v.z, h.z, l.z); split1(v.w, h.w, l.w);
+    sts4(dst_hi, h);
+    sts4(dst_lo, l);
+}
+
+// ---- converter: one thread's share of an operand tile ---------------------------------------------------
+// The raw stage holds the TMA boxes densely, which is exactly "piece i of thread pt at pt*16 + i*8192":
+//   K-major : piece = 16-byte chunk gc = pt & 7 of row (pt >> 3) + 64 i                  (box {32 floats, rows})
+//   MN-major: piece = chunk gc of reduction row (pt >> 3) & 31 of atom 2i + (pt >> 8)    (one {32, 32} box per atom, 4096 B apart)
+// and the operand tile uses the same (row, chunk) with the UMMA swizzle applied to the chunk index.
+template <int LAY, int MODE>
+struct Conv {
+    b200sp_vtensor vt;
+    ActP act;
+    int R, nkb, ac_last, mn_ext;
+    int gc, row, abase, np;
+    uint32_t soff;
+    XfP par;
+    __device__ __forceinline__ void init(const b200sp_vtensor& t, int mn_ext_, int R_, int nkb_, int ac_last_, int pt, int tile_rows) {
+        vt = t; act = act_params(t.act);
+        R = R_; nkb = nkb_; ac_last = ac_last_; mn_ext = mn_ext_;
+        gc = pt & 7;
+        if (LAY == TCG_LAY_KM) {
+            row = pt >> 3; abase = 0;
+            soff = tc::sw128_off(row, gc);
+            const int rem = tile_rows - row;
+            np = rem <= 0 ? 0 : (rem + 63) >> 6;
+        } else {
+            const int atoms = (tile_rows * 4 + 127) / 128;
+            row = (pt >> 3) & 31; abase = pt >> 8;
+            soff = tc::sw128b32_off(row, gc) + abase * 4096;
+            np = (atoms - abase + 1) >> 1;
+        }
+        if (np > APT) np = APT;
+        if (np < 0) np = 0;
+    }
+    // K-major: the transform parameters of k-block kb (channel = reduction index); issue early, the latency hides behind the waits
+    __device__ __forceinline__ void load_params(int kb) {
+        if (LAY == TCG_LAY_KM && MODE != XM_PLAIN) {
+            int ch = kb * 32 + gc * 4;
+            ch = min(ch, R - 4);                 // columns beyond R meet zero-filled B columns: any finite value does
+            xf_load<MODE>(vt, ch, par);
+        }
+    }
+    // raw / raw2: this thread's piece 0 in the raw stage (stage base + operand offset + pt*16); op_hi / op_lo: operand tile bases
+    __device__ __forceinline__ void convert(int kb, int mn0, uint32_t raw, uint32_t raw2, uint32_t op_hi, uint32_t op_lo) {
+        if (LAY == TCG_LAY_KM) {
+            if (kb == nkb - 1 && gc >= ac_last) return;           // partial last k-block: the MMA never reads these chunks
+#pragma unroll
+            for (int i = 0; i < APT; ++i) {
+                if (i < np) {
+                    const float4 r = lds4(raw + i * 8192);
+                    float4 r2 = f4zero();
+                    if (MODE == XM_DY) r2 = lds4(raw2 + i * 8192);
+                    split_store(xf_apply<MODE>(r, r2, par, act), op_hi + soff + i * 8192, op_lo + soff + i * 8192);
+                }
+            }
+        } else {
+            // reduction rows beyond R were zero-filled by the TMA unit, but a transformed zero is not zero: mask them
+            const bool rok = MODE == XM_PLAIN || kb * 32 + row < R;
+#pragma unroll
+            for (int i = 0; i < APT; ++i) {
+                if (i < np) {
+                    const float4 r = lds4(raw + i * 8192);
+                    float4 r2 = f4zero();
+                    if (MODE == XM_DY) r2 = lds4(raw2 + i * 8192);
+                    if (MODE != XM_PLAIN) {
+                        int ch = mn0 + (2 * i + abase) * 32 + gc * 4;
+                        ch = min(ch, mn_ext - 4);
+                        xf_load<MODE>(vt, ch, par);
+                    }
+                    float4 v = xf_apply<MODE>(r, r2, par, act);
+                    if (!rok) v = f4zero();
+                    split_store(v, op_hi + soff + i * 8192, op_lo + soff + i * 8192);
+                }
+            }
+        }
+    }
+};
+
+// TMA boxes of one operand k-block into `dst` (dense, see Conv)
+template <int LAY>
+__device__ __forceinline__ void tma_operand(uint32_t dst, const CUtensorMap* m, uint32_t bar, int mn0, int kb, int atoms) {
+    if (LAY == TCG_LAY_KM) {
+        tma::load_2d(dst, m, bar, kb * 32, mn0);
+    } else {
+        for (int a = 0; a < atoms; ++a) tma::load_2d(dst + a * 4096, m, bar, mn0 + a * 32, kb * 32);
+    }
+}
+
+// =====================================================================================================
+template <int ALAY, int BLAY, int EPI, int AMODE, int BMODE>
+__global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ Tcg2Args g) {
+    using T = float;
+    using E = ETf;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t s_base = tc::smem_u32(smem);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.off_bar);
+    uint64_t* full = bars;                    // [MAX_OP]  converters -> MMA
+    uint64_t* empty = bars + MAX_OP;          // [MAX_OP]  MMA -> converters
+    uint64_t* tfull = bars + 2 * MAX_OP;      // [4]       MMA -> epilogue
+    uint64_t* tempty = bars + 2 * MAX_OP + 4; // [4]       epilogue -> MMA
+    uint64_t* bfull = bars + 2 * MAX_OP + 8;  // [1]       converters -> MMA: resident B converted
+    uint64_t* rawfull = bars + 2 * MAX_OP + 9;             // [MAX_RAW] TMA -> converters
+    uint64_t* rawempty = bars + 2 * MAX_OP + 9 + MAX_RAW;  // [MAX_RAW] converters -> TMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_OP + 9 + 2 * MAX_RAW);
+    int* s_flag = reinterpret_cast<int*>(tmem_slot + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int total = g.numPt * g.numQt * g.splits;
+
+    if (tid == 0) {
+        for (int i = 0; i < MAX_OP; ++i) { tc::mbar_init(&full[i], PROD_T / 32); tc::mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 4; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], g.split_epi ? EPI_W / EPI_SETS : EPI_W); }
+        tc::mbar_init(bfull, PROD_T / 32);
+        for (int i = 0; i < MAX_RAW; ++i) { tc::mbar_init(&rawfull[i], 1); tc::mbar_init(&rawempty[i], PROD_T / 32); }
+        tc::mbar_fence_init();
+    }
+    if (warp == TMA_WARP && lane == 0) {
+        tma::prefetch_map(&g.mapA);
+        if (AMODE == XM_DY) tma::prefetch_map(&g.mapA2);
+        tma::prefetch_map(&g.mapB);
+    }
+    if (warp == MMA_WARP) { tc::tmem_alloc(tmem_slot, g.tmem_cols); tc::tmem_relinquish(); }
+    if (tid < EPI_T) {
+        float* st = reinterpret_cast<float*>(smem + g.off_stat);
+        for (int i = tid; i < EPI_W * 2 * g.BN; i += EPI_T) st[i] = 0.f;
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t b_in_stage = E::NM * g.a_op_bytes;
+    constexpr int slotA2 = APT, slotB = AMODE == XM_DY ? 2 * APT : APT;     // 8192-byte sub-slots of a raw stage: A | [A2] | B
+
+    if (warp == TMA_WARP) {
+        // ======================================= TMA PRODUCER =====================================
+        if (lane == 0) {
+            int rs = 0;
+            uint32_t par = 1;
+            if (g.b_res) {
+                for (int kb = 0; kb < g.nkb; ++kb) {
+                    mbar_wait_guard(&rawempty[rs], par);
+                    tc::mbar_arrive_expect_tx(&rawfull[rs], g.b_tx);
+                    tma_operand<BLAY>(s_base + g.off_raw + rs * g.raw_stage_bytes, &g.mapB, tc::smem_u32(&rawfull[rs]), 0, kb, g.b_atoms);
+                    if (++rs == g.n_raw) { rs = 0; par ^= 1; }
+                }
+            }
+            const uint32_t tx = g.a_tx * (AMODE == XM_DY ? 2u : 1u) + (g.b_res ? 0u : g.b_tx);
+            KIter f;
+            f.init(g, blockIdx.x, total, gridDim.x);
+            while (f.valid()) {
+                mbar_wait_guard(&rawempty[rs], par);
+                const uint32_t rbase = s_base + g.off_raw + rs * g.raw_stage_bytes;
+                const uint32_t bar = tc::smem_u32(&rawfull[rs]);
+                tc::mbar_arrive_expect_tx(&rawfull[rs], tx);
+                tma_operand<ALAY>(rbase, &g.mapA, bar, f.w.p0, f.kb, BM / 32);
+                if (AMODE == XM_DY) tma_operand<ALAY>(rbase + slotA2 * 8192, &g.mapA2, bar, f.w.p0, f.kb, BM / 32);
+                if (!g.b_res) tma_operand<BLAY>(rbase + slotB * 8192, &g.mapB, bar, f.w.q0, f.kb, g.b_atoms);
+                if (++rs == g.n_raw) { rs = 0; par ^= 1; }
+                f.next(g);
+            }
+        }
+    } else if (warp > TMA_WARP) {
+        // ======================================= CONVERTERS =======================================
+        const int pt = tid - PROD_TID0;
+        Conv<ALAY, AMODE> CA;
+        Conv<BLAY, BMODE> CB;
+        CA.init(g.a, g.P, g.R, g.nkb, g.ac_last, pt, BM);
+        CB.init(g.b, g.Q, g.R, g.nkb, g.ac_last, pt, g.BN);
+        const uint32_t raw0 = s_base + g.off_raw + pt * 16;
+        int rs = 0;
+        uint32_t rpar = 0;
+        if (g.b_res) {
+            for (int kb = 0; kb < g.nkb; ++kb) {
+                CB.load_params(kb);
+                mbar_wait_guard(&rawfull[rs], rpar);
+                const uint32_t b_hi = s_base + g.off_bres + kb * (E::NM * g.b_op_bytes), b_lo = b_hi + g.b_op_bytes;
+                CB.convert(kb, 0, raw0 + rs * g.raw_stage_bytes, 0, b_hi, b_lo);
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&rawempty[rs]);
+                if (++rs == g.n_raw) { rs = 0; rpar ^= 1; }
+            }
+            tc::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(bfull);
+        }
+        KIter cons;
+        cons.init(g, blockIdx.x, total, gridDim.x);
+        int os = 0;
+        uint32_t opar = 1;
+        while (cons.valid()) {
+            CA.load_params(cons.kb);
+            if (!g.b_res) CB.load_params(cons.kb);
+            mbar_wait_guard(&rawfull[rs], rpar);
+            mbar_wait_guard(&empty[os], opar);
+            const uint32_t rbase = raw0 + rs * g.raw_stage_bytes;
+            const uint32_t a_hi = s_base + os * g.op_stage_bytes, a_lo = a_hi + g.a_op_bytes;
+            const uint32_t b_hi = a_hi + b_in_stage, b_lo = b_hi + g.b_op_bytes;
+            CA.convert(cons.kb, cons.w.p0, rbase, rbase + slotA2 * 8192, a_hi, a_lo);
+            if (!g.b_res) CB.convert(cons.kb, cons.w.q0, rbase + slotB * 8192, 0, b_hi, b_lo);
+            tc::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) { tc::mbar_arrive(&full[os]); tc::mbar_arrive(&rawempty[rs]); }
+            cons.next(g);
+            if (++rs == g.n_raw) { rs = 0; rpar ^= 1; }
+            if (++os == g.n_op) { os = 0; opar ^= 1; }
+        }
+    } else if (warp == MMA_WARP) {
+        // ======================================= MMA ISSUER ======================================
+        const uint32_t idesc = tc::make_idesc(E::TF32 ? tc::FMT_TF32 : tc::FMT_BF16, ALAY == TCG_LAY_MM, BLAY == TCG_LAY_MM, BM, g.BN);
+        // per-k-step start-address advance (bytes) and LBO / SBO / layout of each operand
+        constexpr uint32_t KSTEP_KM = 32, KSTEP_MM = (E::TF32 ? 8 : 16) * 128;
+        constexpr uint32_t LBO_MM = E::KE * 128, SBO_MM = E::TF32 ? 512 : 1024;
+        constexpr uint32_t LT_MM = E::TF32 ? tc::SWZ_128B_BASE32B : tc::SWZ_128B;
+        // shared-memory descriptors: the high word is a per-operand constant, the low word is (address >> 4) plus the
+        // leading-byte-offset field -- per k-step the issuing thread only adds a constant (it is the serial bottleneck
+        // of short tiles, so every instruction here counts)
+        constexpr uint32_t A_STEP = (ALAY == TCG_LAY_KM ? KSTEP_KM : KSTEP_MM) >> 4, B_STEP = (BLAY == TCG_LAY_KM ? KSTEP_KM : KSTEP_MM) >> 4;
+        constexpr uint32_t A_LBO = ALAY == TCG_LAY_KM ? 0u : ((LBO_MM >> 4) << 16), B_LBO = BLAY == TCG_LAY_KM ? 0u : ((LBO_MM >> 4) << 16);
+        constexpr uint32_t A_HIW = ((ALAY == TCG_LAY_KM ? 1024u : SBO_MM) >> 4) | (1u << 14) | ((uint32_t)(ALAY == TCG_LAY_KM ? tc::SWZ_128B : LT_MM) << 29);
+        constexpr uint32_t B_HIW = ((BLAY == TCG_LAY_KM ? 1024u : SBO_MM) >> 4) | (1u << 14) | ((uint32_t)(BLAY == TCG_LAY_KM ? tc::SWZ_128B : LT_MM) << 29);
+        auto mk = [](uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); };
+        if (g.b_res) { mbar_wait_guard(bfull, 0, g.wait_mode); tc::tc_fence_after(); }
+        int os = 0, acc = 0, tlm = 0;
+        uint32_t fpar = 0, tpar = 1;
+        for (int it = blockIdx.x; it < total; it += gridDim.x) {
+            const Item w = get_item(g, it);
+            mbar_wait_guard(&tempty[acc], tpar, g.wait_mode);
+            tc::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * g.acc_cols;
+            // 3xTF32: the two correction products (lo*hi, hi*lo) go to a SECOND accumulator and are added in fp32-RN by the
+            // epilogue.  tcgen05 accumulates with round-toward-zero, so every MMA into the large accumulator costs up to one
+            // ulp of bias; keeping the small terms out of it cuts the number of such truncations from 3K/8 to K/8.
+            const uint32_t d_corr = d_tmem + (g.acc_cols > g.BN ? g.BN : 0);
+            for (int kb = w.kb0; kb < w.kb1; ++kb) {
+                if (lane == 0) TL(4, tlm);
+                mbar_wait_guard(&full[os], fpar, g.wait_mode);
+                tc::tc_fence_after();
+                if (lane == 0) TL(5, tlm);
+                if (lane == 0) {
+                    const uint32_t a_hi = s_base + os * g.op_stage_bytes, a_lo = a_hi + g.a_op_bytes;
+                    const uint32_t b_hi = g.b_res ? s_base + g.off_bres + kb * (E::NM * g.b_op_bytes) : a_hi + b_in_stage;
+                    const uint32_t b_lo = b_hi + g.b_op_bytes;
+                    // a K-major operand only holds the active chunks of a partial last k-block: never read beyond them
+                    const int nks = ((ALAY == TCG_LAY_KM || BLAY == TCG_LAY_KM) && kb == g.nkb - 1) ? g.nks_last : 4;
+                    const uint32_t al = (a_lo >> 4) + A_LBO, ah = (a_hi >> 4) + A_LBO, bl = (b_lo >> 4) + B_LBO, bh = (b_hi >> 4) + B_LBO;
+                    const uint32_t first = kb > w.kb0 ? 1u : 0u;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        if (ks < nks) {
+                            const uint32_t accum = ks > 0 ? 1u : first;
+                            if (E::TF32) {
+                                const bool split = g.acc_cols > g.BN;
+                                tc::umma<true>(d_corr, mk(al + ks * A_STEP, A_HIW), mk(bh + ks * B_STEP, B_HIW), idesc, accum);
+                                tc::umma<true>(d_corr, mk(ah + ks * A_STEP, A_HIW), mk(bl + ks * B_STEP, B_HIW), idesc, 1u);
+                                tc::umma<true>(d_tmem, mk(ah + ks * A_STEP, A_HIW), mk(bh + ks * B_STEP, B_HIW), idesc, split ? accum : 1u);
+                            } else {
+                                tc::umma<false>(d_tmem, mk(ah + ks * A_STEP, A_HIW), mk(bh + ks * B_STEP, B_HIW), idesc, accum);
+                            }
+                        }
+                    }
+                    tc::umma_commit(&empty[os]);
+                    if (kb == w.kb1 - 1) tc::umma_commit(&tfull[acc]);
+                    TL(6, tlm);
+                }
+                ++tlm;
+                __syncwarp();
+                if (++os == g.n_op) { os = 0; fpar ^= 1; }
+            }
+            if (++acc == g.nacc) { acc = 0; tpar ^= 1; }
+        }
+    } else {
+        // ======================================= EPILOGUE ========================================
+        const int lq = warp & 3, half = warp >> 2;      // TMEM lane quarter, column-chunk parity
+        float* stg = reinterpret_cast<float*>(smem + g.off_stg) + warp * (32 * STG_LD);
+        const uint32_t stg_u = tc::smem_u32(stg);
+        float* stat_all = reinterpret_cast<float*>(smem + g.off_stat);      // [EPI_W][2][BN]
+        float* stat = stat_all + warp * (2 * g.BN);
+        const bool do_stats = (EPI == TCG_EPI_FWD && g.has_bnf) || (EPI == TCG_EPI_DGRAD && g.has_bnb && g.bnb.s1 != nullptr);
+        const bool plain_out = EPI == TCG_EPI_FWD && g.bias == nullptr && g.out_act == B200SP_ACT_NONE;
+        const int cq = lane & 7, rs = lane >> 3;
+        const ActP oact = act_params(EPI == TCG_EPI_FWD ? g.out_act : g.bnb.act);
+        T* outT = reinterpret_cast<T*>(g.out);
+        float* outF = reinterpret_cast<float*>(g.out);
+        const int nchunks = (g.BN + 31) >> 5;
+        int last_chunk = -1;                            // last chunk this warp reads from TMEM
+        const int c_first = g.split_epi ? 0 : half, c_step = g.split_epi ? 1 : EPI_SETS;
+        for (int c = c_first; c < nchunks; c += c_step) last_chunk = c;
+        int ni = 0;
+        int cur_q0 = -1;
+        auto flush = [&](int q0) {
+            epi_bar();
+            for (int c = tid; c < g.BN; c += EPI_T) {
+                double a = 0.0, b = 0.0;
+#pragma unroll
+                for (int w = 0; w < EPI_W; ++w) {
+                    a += (double)stat_all[w * 2 * g.BN + c];
+                    b += (double)stat_all[w * 2 * g.BN + g.BN + c];
+                    stat_all[w * 2 * g.BN + c] = 0.f;
+                    stat_all[w * 2 * g.BN + g.BN + c] = 0.f;
+                }
+                if (q0 + c < g.Q) {
+                    if (EPI == TCG_EPI_FWD) { atomicAdd(g.bnf.sum + q0 + c, a); atomicAdd(g.bnf.sumsq + q0 + c, b); }
+                    else                    { atomicAdd(g.bnb.s1 + q0 + c, a);  atomicAdd(g.bnb.s2 + q0 + c, b); }
+                }
+            }
+            epi_bar();
+        };
+        int acc = -1;
+        uint32_t tpar = 1;
+        for (int it = blockIdx.x; it < total; it += gridDim.x, ++ni) {
+            if (++acc == g.nacc) acc = 0;
+            if (acc == 0) tpar ^= 1;
+            if (g.split_epi && (ni & 1) != half) continue;      // the other warp set drains this tile
+            const Item w = get_item(g, it);
+            if (do_stats && cur_q0 >= 0 && cur_q0 != w.q0) flush(cur_q0);
+            cur_q0 = w.q0;
+            mbar_wait_sleep(&tfull[acc], tpar, g.epi_sleep);
+            tc::tc_fence_after();
+            const uint32_t t_row = tmem_base + acc * g.acc_cols + ((uint32_t)(lq * 32) << 16);
+            const bool split_acc = g.acc_cols > g.BN;
+            if (last_chunk < 0) {                        // nothing to read for this warp: release immediately
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&tempty[acc]);
+            }
+            for (int ci = c_first; ci < nchunks; ci += c_step) {
+                const int c0 = ci * 32;
+                const int ncol = min(32, g.BN - c0);
+                uint32_t r[32];
+                if (ncol == 32) {
+                    tc::tmem_ld32(t_row + c0, r);
+                } else {
+                    uint32_t r16[16];
+                    tc::tmem_ld16(t_row + c0, r16);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { r[i] = r16[i]; r[16 + i] = 0u; }
+                }
+                tc::tmem_ld_wait();
+                if (split_acc) {                // add the correction accumulator (fp32 round-to-nearest), 16 columns at a time
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        if (hh * 16 < ncol) {
+                            uint32_t q16[16];
+                            tc::tmem_ld16(t_row + g.BN + c0 + hh * 16, q16);
+                            tc::tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) r[hh * 16 + i] = __float_as_uint(__uint_as_float(r[hh * 16 + i]) + __uint_as_float(q16[i]));
+                        }
+                    }
+                }
+                if (ci == last_chunk) {         // accumulator drained by this warp: hand TMEM back to the MMA warp
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&tempty[acc]);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    sts4(stg_u + (lane * STG_LD + 4 * j) * 4,
+                         make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+                __syncwarp();
+                // ---- coalesced phase: lane = (row sub-index rs, column quad cq) ----
+                const int col = w.q0 + c0 + 4 * cq;
+                const bool cok = 4 * cq < ncol && col < g.Q;
+                float4 bias4 = f4zero(), sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sh4 = f4zero(), mu4 = f4zero(), rs4 = f4zero();
+                if (cok) {
+                    if (EPI == TCG_EPI_FWD && g.bias) bias4 = ldg4(g.bias + col);
+                    if (EPI == TCG_EPI_DGRAD && g.has_bnb) {
+                        if (g.bnb.scale) { sc4 = ldg4(g.bnb.scale + col); sh4 = ldg4(g.bnb.shift + col); }
+                        if (g.bnb.s1) { mu4 = ldg4(g.bnb.mean + col); rs4 = ldg4(g.bnb.rstd + col); }
+                    }
+                }
+                float4 ls = f4zero(), lq4 = f4zero();
+                const int row_base = w.p0 + lq * 32 + rs;
+                // rows are handled in two batches of four so that the global loads of the dgrad epilogue (saved conv
+                // output y for the activation mask / BN reductions, skip gradient) are all in flight together
+                // instead of one dependent round trip per row
+#pragma unroll
+                for (int hb = 0; hb < 2; ++hb) {
+                    float4 yv[4], sv[4];
+                    if (EPI == TCG_EPI_DGRAD) {
+#pragma unroll
+                        for (int p4 = 0; p4 < 4; ++p4) {
+                            const int row = row_base + (hb * 4 + p4) * 4;
+                            const bool ok = cok && row < g.P;
+                            const size_t off = (size_t)row * g.ldo + col;
+                            yv[p4] = (g.has_bnb && ok) ? Vec4<T>::ld(reinterpret_cast<const T*>(g.bnb.y) + off) : f4zero();
+                            sv[p4] = (g.skip && ok) ? Vec4<T>::ld(reinterpret_cast<const T*>(g.skip) + off) : f4zero();
+                        }
+                    }
+#pragma unroll
+                    for (int p4 = 0; p4 < 4; ++p4) {
+                        const int ps = hb * 4 + p4;
+                        const int trow = ps * 4 + rs;
+                        const int row = row_base + ps * 4;
+                        if (!(cok && row < g.P)) continue;
+                        float4 v = lds4(stg_u + (trow * STG_LD + 4 * cq) * 4);
+                        const size_t off = (size_t)row * g.ldo + col;
+                        if (EPI == TCG_EPI_FWD) {
+                            if (!plain_out) {
+                                v.x = act_fwd(v.x + bias4.x, oact); v.y = act_fwd(v.y + bias4.y, oact);
+                                v.z = act_fwd(v.z + bias4.z, oact); v.w = act_fwd(v.w + bias4.w, oact);
+                            }
+                            Vec4<T>::st(outT + off, v);
+                            if (!E::TF32) {      // statistics of the value as stored (bf16-rounded)
+                                v.x = __bfloat162float(__float2bfloat16_rn(v.x)); v.y = __bfloat162float(__float2bfloat16_rn(v.y));
+                                v.z = __bfloat162float(__float2bfloat16_rn(v.z)); v.w = __bfloat162float(__float2bfloat16_rn(v.w));
+                            }
+                            ls.x += v.x; ls.y += v.y; ls.z += v.z; ls.w += v.w;
+                            lq4.x = fmaf(v.x, v.x, lq4.x); lq4.y = fmaf(v.y, v.y, lq4.y); lq4.z = fmaf(v.z, v.z, lq4.z); lq4.w = fmaf(v.w, v.w, lq4.w);
+                        } else if (EPI == TCG_EPI_DGRAD) {
+                            v.x *= g.scale_out; v.y *= g.scale_out; v.z *= g.scale_out; v.w *= g.scale_out;
+                            const float4 sk = sv[p4];
+                            v.x += sk.x; v.y += sk.y; v.z += sk.z; v.w += sk.w;
+                            if (g.has_bnb) {
+                                const float4 y = yv[p4];
+                                v.x *= act_bwd(fmaf(y.x, sc4.x, sh4.x), oact); v.y *= act_bwd(fmaf(y.y, sc4.y, sh4.y), oact);
+                                v.z *= act_bwd(fmaf(y.z, sc4.z, sh4.z), oact); v.w *= act_bwd(fmaf(y.w, sc4.w, sh4.w), oact);
+                                ls.x += v.x; ls.y += v.y; ls.z += v.z; ls.w += v.w;
+                                lq4.x = fmaf(v.x, (y.x - mu4.x) * rs4.x, lq4.x); lq4.y = fmaf(v.y, (y.y - mu4.y) * rs4.y, lq4.y);
+                                lq4.z = fmaf(v.z, (y.z - mu4.z) * rs4.z, lq4.z); lq4.w = fmaf(v.w, (y.w - mu4.w) * rs4.w, lq4.w);
+                            }
+                            Vec4<T>::st(outT + off, v);
+                        } else {
+                            // one 16-byte vector reduction instead of four scalar atomics (sm_90+: red.global.add.v4.f32)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(outF + off), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                                         : "memory");
+                        }
+                    }
+                }
+                if (do_stats) {
+#pragma unroll
+                    for (int o = 8; o < 32; o <<= 1) {
+                        ls.x += __shfl_xor_sync(0xffffffffu, ls.x, o); ls.y += __shfl_xor_sync(0xffffffffu, ls.y, o);
+                        ls.z += __shfl_xor_sync(0xffffffffu, ls.z, o); ls.w += __shfl_xor_sync(0xffffffffu, ls.w, o);
+                        lq4.x += __shfl_xor_sync(0xffffffffu, lq4.x, o); lq4.y += __shfl_xor_sync(0xffffffffu, lq4.y, o);
+                        lq4.z += __shfl_xor_sync(0xffffffffu, lq4.z, o); lq4.w += __shfl_xor_sync(0xffffffffu, lq4.w, o);
+                    }
+                    if (rs == 0 && 4 * cq < ncol) {
+                        float* s0 = stat + c0 + 4 * cq;
+                        float* s1 = stat + g.BN + c0 + 4 * cq;
+                        s0[0] += ls.x; s0[1] += ls.y; s0[2] += ls.z; s0[3] += ls.w;
+                        s1[0] += lq4.x; s1[1] += lq4.y; s1[2] += lq4.z; s1[3] += lq4.w;
+                    }
+                }
+                __syncwarp();      // staging tile is reused by the next column chunk
+            }
+        }
+        if (do_stats) {
+            flush(cur_q0 >= 0 ? cur_q0 : 0);       // every epilogue warp takes part (bar.sync), even one that drained no tile
+            // elect the last CTA of the grid: it turns the accumulated sums into scale/shift (fwd) or dy coefficients (bwd)
+            __threadfence();
+            epi_bar();
+            if (tid == 0) {
+                uint32_t* ticket = EPI == TCG_EPI_FWD ? g.bnf.ticket : g.bnb.ticket;
+                const uint32_t t = atomicAdd(ticket, 1u);
+                const int last = (t == gridDim.x - 1);
+                if (last) *ticket = 0u;
+                *s_flag = last;
+            }
+            epi_bar();
+            if (*s_flag) {
+                __threadfence();
+                for (int c = tid; c < g.Q; c += EPI_T) {
+                    if (EPI == TCG_EPI_FWD) bn_fwd_finalize_channel(g.bnf, c, g.count);
+                    else                    bn_bwd_finalize_channel(g.bnb, c, g.count);
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    if (warp == MMA_WARP) tc::tmem_dealloc(tmem_base, g.tmem_cols);
+}
+
+// -------------------------------------------------------------------------------------------------
+constexpr uint32_t SMEM_LIMIT = 227 * 1024;
+constexpr uint32_t BRES_LIMIT = 64 * 1024;
+
+// raw fp32 operand stored [rows][ld] with `cols` valid columns: box {32 floats, box_rows}, no swizzle, zero fill
+inline int encode_f32(CUtensorMap* m, const void* base, int cols, int rows, int ld, int box_rows) {
+    tma::EncodeTiledFn fn = tma::encode_fn();
+    if (!fn) return B200SP_ENOSYS;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : B200SP_ENOSYS;
+}
+
+template <int ALAY, int BLAY, int EPI, int AMODE, int BMODE>
+int launch_cfg(Tcg2Args& a, cudaStream_t st) {
+    using E = ETf;
+    static bool attr_set = false;
+    auto kern = tcgemm2_kernel<ALAY, BLAY, EPI, AMODE, BMODE>;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int numPt = ceil_div(a.P, BM);
+    a.nkb = ceil_div(a.R, E::KE);
+    {
+        const int rem = a.R - (a.nkb - 1) * E::KE;
+        a.nks_last = ceil_div(rem, 2 * E::EPV);
+        a.ac_last = 2 * a.nks_last;
+    }
+    // ---- tile width: the widest that fits shared memory; narrower while the grid does not cover the machine ----
+    bool fits = false;
+    for (int cap = 128; cap >= 32 && !fits; cap -= (cap > 64 ? 32 : 16)) {
+        int numQt = ceil_div(a.Q, cap);
+        int BN = ceil_div(ceil_div(a.Q, numQt), 16) * 16;
+        if (EPI != TCG_EPI_ATOMIC) {
+            while (numPt * numQt < NUM_SMS && BN > 32) {
+                ++numQt;
+                BN = ceil_div(ceil_div(a.Q, numQt), 16) * 16;
+            }
+        }
+        numQt = ceil_div(a.Q, BN);
+        a.BN = BN; a.numPt = numPt; a.numQt = numQt;
+        a.a_op_bytes = BM * 128;
+        a.b_atoms = ceil_div(BN * E::ES, 128);
+        a.b_op_bytes = BLAY == TCG_LAY_KM ? BN * 128 : a.b_atoms * E::KE * 128;
+        const int nb_slots = ceil_div((int)a.b_op_bytes, 8192);
+        const uint32_t bres_bytes = (uint32_t)a.nkb * E::NM * a.b_op_bytes;
+        a.b_res = (EPI != TCG_EPI_ATOMIC && numQt == 1 && BMODE == XM_PLAIN && bres_bytes <= BRES_LIMIT) ? 1 : 0;
+        a.op_stage_bytes = E::NM * (a.a_op_bytes + (a.b_res ? 0 : a.b_op_bytes));
+        a.raw_stage_bytes = (APT + (AMODE == XM_DY ? APT : 0) + (a.b_res ? 0 : nb_slots)) * 8192;
+        if (a.b_res && a.raw_stage_bytes < (uint32_t)nb_slots * 8192) a.raw_stage_bytes = nb_slots * 8192;
+        const uint32_t fixed = EPI_W * 32 * STG_LD * 4 + EPI_W * 2 * BN * 4 + 256 + (a.b_res ? bres_bytes : 0);
+        a.n_op = 2;
+        a.n_raw = 0;
+        for (int nr = MAX_RAW; nr >= 2; --nr) {
+            if (a.n_op * a.op_stage_bytes + nr * a.raw_stage_bytes + fixed + 1088 <= SMEM_LIMIT) { a.n_raw = nr; break; }
+        }
+        if (a.n_raw == 0) continue;
+        fits = true;
+        while (a.n_op < MAX_OP && (a.n_op + 1) * a.op_stage_bytes + a.n_raw * a.raw_stage_bytes + fixed + 1088 <= SMEM_LIMIT) ++a.n_op;
+        a.off_bres = a.n_op * a.op_stage_bytes;
+        a.off_raw = a.off_bres + (a.b_res ? bres_bytes : 0);
+        a.off_stg = a.off_raw + a.n_raw * a.raw_stage_bytes;
+        a.off_stat = a.off_stg + EPI_W * 32 * STG_LD * 4;
+        a.off_bar = (a.off_stat + EPI_W * 2 * BN * 4 + 15) & ~15u;
+    }
+    if (!fits) return B200SP_ENOSYS;
+    const int numQt = a.numQt, BN = a.BN;
+    a.splits = 1;
+    if (EPI == TCG_EPI_ATOMIC) {
+        const int base = numPt * numQt;
+        int s = ceil_div(2 * NUM_SMS, base);
+        const int smax = a.nkb / 4 > 0 ? a.nkb / 4 : 1;
+        if (s > smax) s = smax;
+        if (s < 1) s = 1;
+        a.splits = s;
+    }
+    a.kb_per_split = ceil_div(a.nkb, a.splits);
+    a.splits = ceil_div(a.nkb, a.kb_per_split);
+    const uint32_t smem = a.off_bar + 256 + 1024;
+    a.acc_cols = (2 * 2 * BN <= 512) ? 2 * BN : BN;
+    a.nacc = 4 * a.acc_cols <= 512 ? 4 : 2;
+    a.split_epi = (BN <= 32 && numQt == 1 && EPI_SETS == 2) ? 1 : 0;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(a.nacc * a.acc_cols)) cols <<= 1;
+    a.tmem_cols = cols;
+    // ---- tensor maps of the raw operands ----
+    int rc;
+    if (ALAY == TCG_LAY_KM) { rc = encode_f32(&a.mapA, a.a.x, a.R, a.P, a.lda, BM); a.a_tx = BM * 128; }
+    else                    { rc = encode_f32(&a.mapA, a.a.x, a.P, a.R, a.lda, 32); a.a_tx = (BM / 32) * 4096; }
+    if (rc) return rc;
+    if (AMODE == XM_DY) {
+        rc = ALAY == TCG_LAY_KM ? encode_f32(&a.mapA2, a.a.x2, a.R, a.P, a.lda, BM) : encode_f32(&a.mapA2, a.a.x2, a.P, a.R, a.lda, 32);
+        if (rc) return rc;
+    } else {
+        a.mapA2 = a.mapA;
+    }
+    if (BLAY == TCG_LAY_KM) { rc = encode_f32(&a.mapB, a.b.x, a.R, a.Q, a.ldb, BN); a.b_tx = BN * 128; }
+    else                    { rc = encode_f32(&a.mapB, a.b.x, a.Q, a.R, a.ldb, 32); a.b_tx = a.b_atoms * 4096; }
+    if (rc) return rc;
+    const int total = numPt * numQt * a.splits;
+    const int grid = total < NUM_SMS ? total : NUM_SMS;
+    kern<<<grid, NT, smem, st>>>(a);
+    B200SP_COUNT_LAUNCH();
+    B200SP_RETURN_LAST();
+}
+
+}  // namespace
+
+int tcgemm2_launch(const TcgProblem& p, cudaStream_t st) {
+    if (p.dtype != B200SP_F32) return B200SP_ENOSYS;
+    if (p.Q % 4 || p.lda % 4 || p.ldb % 4) return B200SP_ENOSYS;
+    if (p.a_lay == TCG_LAY_KM ? (p.R % 4) : (p.P % 4)) return B200SP_ENOSYS;
+    if (p.b_lay == TCG_LAY_KM ? (p.R % 4) : (p.Q % 4)) return B200SP_ENOSYS;
+    if (p.b.mode == B200SP_VT_DY) return B200SP_ENOSYS;
+    if (((uintptr_t)p.a.x | (uintptr_t)p.b.x | (uintptr_t)p.a.x2 | (uintptr_t)p.out) & 15) return B200SP_ENOSYS;
+    if ((p.a.mode == B200SP_VT_BNACT && p.a.act == B200SP_ACT_SIGMOID) || (p.b.mode == B200SP_VT_BNACT && p.b.act == B200SP_ACT_SIGMOID)) return B200SP_ENOSYS;
+    Tcg2Args a;
+    memset(&a, 0, sizeof(a));
+    a.a = p.a; a.b = p.b;
+    a.P = p.P; a.Q = p.Q; a.R = p.R; a.lda = p.lda; a.ldb = p.ldb;
+    a.ldo = p.ldo > 0 ? p.ldo : p.Q;
+    if (a.ldo % 4) return B200SP_ENOSYS;
+    a.out = p.out; a.bias = p.bias; a.out_act = p.out_act;
+    a.has_bnf = p.bnf != nullptr;
+    if (p.bnf) a.bnf = *p.bnf;
+    a.skip = p.skip; a.scale_out = p.scale_out;
+    a.has_bnb = p.bnb != nullptr;
+    if (p.bnb) a.bnb = *p.bnb;
+    a.count = p.count;
+    a.epi_sleep = 512;
+    const int am = p.a.mode, bm = p.b.mode;
+    if (p.epi == TCG_EPI_FWD && p.a_lay == TCG_LAY_KM && p.b_lay == TCG_LAY_KM && bm == B200SP_VT_PLAIN) {
+        if (am == B200SP_VT_PLAIN) return launch_cfg<TCG_LAY_KM, TCG_LAY_KM, TCG_EPI_FWD, XM_PLAIN, XM_PLAIN>(a, st);
+        if (am == B200SP_VT_BNACT) return launch_cfg<TCG_LAY_KM, TCG_LAY_KM, TCG_EPI_FWD, XM_BNACT, XM_PLAIN>(a, st);
+    }
+    if (p.epi == TCG_EPI_DGRAD && p.a_lay == TCG_LAY_KM && p.b_lay == TCG_LAY_MM && bm == B200SP_VT_PLAIN) {
+        if (am == B200SP_VT_PLAIN) return launch_cfg<TCG_LAY_KM, TCG_LAY_MM, TCG_EPI_DGRAD, XM_PLAIN, XM_PLAIN>(a, st);
+        if (am == B200SP_VT_DY) return launch_cfg<TCG_LAY_KM, TCG_LAY_MM, TCG_EPI_DGRAD, XM_DY, XM_PLAIN>(a, st);
+    }
+    if (p.epi == TCG_EPI_ATOMIC && p.a_lay == TCG_LAY_MM && p.b_lay == TCG_LAY_MM) {
+        if (am == B200SP_VT_PLAIN && bm == B200SP_VT_PLAIN) return launch_cfg<TCG_LAY_MM, TCG_LAY_MM, TCG_EPI_ATOMIC, XM_PLAIN, XM_PLAIN>(a, st);
+        if (am == B200SP_VT_PLAIN && bm == B200SP_VT_BNACT) return launch_cfg<TCG_LAY_MM, TCG_LAY_MM, TCG_EPI_ATOMIC, XM_PLAIN, XM_BNACT>(a, st);
+        if (am == B200SP_VT_DY && bm == B200SP_VT_PLAIN) return launch_cfg<TCG_LAY_MM, TCG_LAY_MM, TCG_EPI_ATOMIC, XM_DY, XM_PLAIN>(a, st);
+        if (am == B200SP_VT_DY && bm == B200SP_VT_BNACT) return launch_cfg<TCG_LAY_MM, TCG_LAY_MM, TCG_EPI_ATOMIC, XM_DY, XM_BNACT>(a, st);
+    }
+    return B200SP_ENOSYS;
+}
