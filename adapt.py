@@ -15,15 +15,16 @@ logger = logging.getLogger(__name__)
 def main():
     from speedplusbaseline_b200 import cli
     from speedplusbaseline_b200.utils import set_all_seeds, save_checkpoint
+    from speedplusbaseline_b200 import dist as D
     device = cli.select_device(cfg)
     assert cfg.dann and cfg.model_name == 'krn'
-    set_all_seeds(2021, cfg, True)
+    set_all_seeds(2021 + D.rank(), cfg, True)           # adapt.py:53 fixes 2021; ranks > 0 offset it (weights are broadcast below)
     cli.setup_logger('train')
     os.makedirs(cfg.savedir, exist_ok=True)
     os.makedirs(cfg.logdir, exist_ok=True)
     try:
         from torch.utils.tensorboard import SummaryWriter
-        writer = SummaryWriter(cfg.logdir)
+        writer = SummaryWriter(cfg.logdir) if D.is_main() else None
     except Exception:
         writer = None
     with open(os.path.join(cfg.savedir, 'config.txt'), 'w') as f:
@@ -36,6 +37,7 @@ def main():
         from src.nets.build import get_model, get_optimizer
         from src.core.dann import train_dann_single_epoch_krn
     model = get_model(cfg)
+    D.broadcast_model(model)
     optimizer = get_optimizer(cfg, model)
     lr_scheduler = torch.optim.lr_scheduler.StepLR(optimizer, step_size=cfg.lr_decay_step, gamma=cfg.lr_decay_alpha)
     begin_epoch = cli.resume(cfg, model, optimizer, device)
@@ -53,10 +55,15 @@ def main():
         perf = epoch + 1
         is_best = perf > best_perf
         best_perf = max(best_perf, perf)
+        if not D.is_main():                          # replicas are identical after every step: rank 0 writes the checkpoint
+            continue
         save_checkpoint({'epoch': epoch + 1, 'model': cfg.model_name, 'state_dict': model.state_dict(),
                          'best_score': best_perf, 'optimizer': optimizer.state_dict()}, is_best, cfg.savedir)
     if writer is not None:
         writer.close()
+    if D.world_size() > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == '__main__':

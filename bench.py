@@ -4,7 +4,8 @@
     python bench.py --gpus 1 --steps 30 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference ...      # the reference's algorithm on the host CPU (oracle port)
+    python bench.py --impl reference ...      # the UNMODIFIED reference loop (baseline/_ref) on the host CPU
+    python bench.py --workload dann --gpus N  # BASELINE.json configs[3]: the adapt.py step (secondary line)
 
 Workload = BASELINE.json configs[1]: KRN train, bs=48/GPU, AdamW (lr 1e-3, betas .9/.999, wd .01),
 clip_grad_norm 1.0, 224x224 synthetic images in [0,1), random-init weights (no network for ImageNet).
@@ -73,54 +74,89 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
+def _ref_runner():
+    sys.path.insert(0, os.path.join(ROOT, 'baseline'))
+    import ref_runner
+    return ref_runner if ref_runner.available() else None
+
+
+def _reference_cpu(warmup, steps, budget_s=200.0):
+    """The reference's own train_single_epoch_krn (unmodified, staged under baseline/_ref) on the host cores; falls back to the
+    oracle port when the staged copy is absent.  Every step is a full bs=48 iteration; the number of timed steps is the one
+    asked for unless that would exceed `budget_s` (stated in the result)."""
+    import torch
+    cores = os.cpu_count() or 1
+    R = _ref_runner()
+    if R is not None:
+        # a bs=48 iteration costs ~0.7-1 s on 16 host cores: the step count is bounded a priori so the run ends in minutes
+        w, k = max(1, warmup), max(1, min(steps, int(budget_s)))
+        r = R.time_krn_train('cpu', batch=BATCH, hw=HW, warmup=w, steps=k, threads=cores)
+        r.update(kind='reference', warmup=w, steps=k, cores=cores,
+                 sample='%d full bs=%d iterations of the unmodified reference loop src/core/trainer.py:train_single_epoch_krn '
+                        '(torch %s CPU kernels, %d threads), after %d warm-up iterations' % (k, BATCH, torch.__version__, cores, w))
+        return r
+    from oracle import krn as okrn, synth, steps as osteps
+    torch.set_num_threads(cores)
+    sd = synth.synth_state_dict(okrn.krn_shapes(), 2021)
+    st = osteps.new_state(sd)
+    x, y = synth.synth_images(BATCH), synth.synth_keypoints(BATCH)
+    w = max(1, warmup)
+    t0 = time.perf_counter()
+    for _ in range(w):
+        osteps.krn_train_step(sd, st, x, y)
+    per = (time.perf_counter() - t0) / w
+    k = max(1, min(steps, int(budget_s / max(per, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(k):
+        osteps.krn_train_step(sd, st, x, y)
+    dt = (time.perf_counter() - t0) / k
+    return {'ms_per_step': dt * 1e3, 'images_per_sec': BATCH / dt, 'kind': 'port', 'warmup': w, 'steps': k, 'cores': cores,
+            'sample': '%d full bs=%d train steps of the oracle port (baseline/_ref not staged), %d threads' % (k, BATCH, cores)}
+
+
 def run_reference(args):
-    """The reference's algorithm on the host cores: oracle port (oracle/steps.py), all threads."""
+    """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores (rank 0 only)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    import torch
-    from oracle import krn as okrn, synth, steps
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    sd = synth.synth_state_dict(okrn.krn_shapes(), 2021)
-    st = steps.new_state(sd)
-    x, y = synth.synth_images(BATCH), synth.synth_keypoints(BATCH)
-    for _ in range(max(1, min(args.warmup, 2))):
-        steps.krn_train_step(sd, st, x, y)
-    k = max(1, min(args.steps, 5))
-    t0 = time.perf_counter()
-    for _ in range(k):
-        steps.krn_train_step(sd, st, x, y)
-    dt = (time.perf_counter() - t0) / k
-    v = BATCH / dt
-    sample = '%d full bs=%d train steps of the oracle port (torch CPU ops, %d threads)' % (k, BATCH, cores)
+    r = _reference_cpu(args.warmup, args.steps)
+    v = r['images_per_sec']
     print(json.dumps({
-        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': k,
-        'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': r['steps'],
+        'warmup': r['warmup'], 'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
-        'config': {'workload': 'KRN train bs=48 AdamW 224x224 synthetic (BASELINE.json configs[1])', 'device': 'host CPU'},
-        'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'config': {'workload': 'KRN train bs=48 AdamW 224x224 synthetic (BASELINE.json configs[1])', 'device': 'host CPU',
+                   'requested_steps': args.steps, 'requested_warmup': args.warmup},
+        'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': r['cores'], 'kind': r['kind'], 'sample': r['sample']},
         'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
 
-def cpu_baseline(steps_n=3):
-    import torch
-    from oracle import krn as okrn, synth, steps
-    cores = os.cpu_count() or 1
-    nt = torch.get_num_threads()
-    torch.set_num_threads(cores)
-    sd = synth.synth_state_dict(okrn.krn_shapes(), 2021)
-    st = steps.new_state(sd)
-    x, y = synth.synth_images(BATCH), synth.synth_keypoints(BATCH)
-    steps.krn_train_step(sd, st, x, y)
-    t0 = time.perf_counter()
-    for _ in range(steps_n):
-        steps.krn_train_step(sd, st, x, y)
-    dt = (time.perf_counter() - t0) / steps_n
-    torch.set_num_threads(nt)
-    return {'value': BATCH / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-            'sample': '%d full bs=%d KRN train steps of the oracle port (torch CPU, %d threads), %.2f s/step' % (steps_n, BATCH, cores, dt)}
+def cpu_baseline():
+    r = _reference_cpu(2, 15, budget_s=25.0)
+    return {'value': r['images_per_sec'], 'unit': UNIT, 'cores': r['cores'], 'kind': r['kind'], 'sample': r['sample'],
+            'ms_per_step': r['ms_per_step']}
 
+
+def reference_cuda(dev_index=0):
+    """The bar the product path has to beat: the UNMODIFIED reference through its own loop on the same GPU --
+    stock PyTorch dispatch to cuDNN / cuBLAS, fp32 and `--use_fp16` (torch.cuda.amp autocast + GradScaler), 20 warm-up +
+    100 timed iterations, wall clock around the loop with a device synchronize on both sides."""
+    R = _ref_runner()
+    if R is None:
+        return {'unavailable': 'baseline/_ref not staged (python tools/stage_reference.py)'}
+    dev = 'cuda:%d' % dev_index
+    out = {}
+    for key, kw in (('reference_cuda_fp32', {}), ('reference_cuda_amp', {'fp16': True})):
+        try:
+            out[key] = R.time_krn_train(dev, batch=BATCH, hw=HW, warmup=20, steps=100, **kw)
+        except Exception as e:
+            out[key] = {'error': repr(e)[:200]}
+    try:
+        out['reference_cuda_dann_fp32'] = R.time_dann_train(dev, batch=BATCH, hw=HW, warmup=10, steps=50)
+        out['reference_cuda_styleaug_fwd'] = R.time_styleaug(dev, batch=BATCH, hw=HW, warmup=5, steps=30)
+    except Exception as e:
+        out['reference_cuda_other'] = {'error': repr(e)[:200]}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -150,10 +186,15 @@ def secondary_workloads(dev, stepper, d_img, d_tgt, k=8):
     from speedplusbaseline_b200.core.trainer import SPNTrainStep
     out = {}
     from speedplusbaseline_b200.styleaug.ghiasi import synthetic_state
-    state = synthetic_state(7)                                   # random Ghiasi weights + embedding statistics (no checkpoint files here)
-    aug = StyleAugmentor(0.5, dev, state=state)
+    from speedplusbaseline_b200.styleaug.styleAugmentor import checkpoint_dir
+    try:                                                         # the reference's REAL checkpoints (staged with baseline/_ref)
+        checkpoint_dir()
+        aug, weights = StyleAugmentor(0.5, dev), 'real checkpoints (baseline/_ref/src/styleaug/checkpoints)'
+    except FileNotFoundError:
+        aug, weights = StyleAugmentor(0.5, dev, state=synthetic_state(7)), 'synthetic (checkpoints not staged)'
     ms = _time_steps(lambda: aug(d_img), 2, k)
-    out['styleaug_forward_bs48'] = {'ms': ms, 'images_per_sec': BATCH / ms * 1e3, 'tflops_reference_flops': 15.434 * BATCH / ms}
+    out['styleaug_forward_bs48'] = {'ms': ms, 'images_per_sec': BATCH / ms * 1e3, 'tflops_reference_flops': 15.434 * BATCH / ms,
+                                    'weights': weights}
     ms = _time_steps(lambda: stepper.step(aug(d_img), d_tgt), 2, k)
     out['krn_train_with_styleaug_ratio1_bs48'] = {'ms': ms, 'images_per_sec': BATCH / ms * 1e3}
     del aug
@@ -205,13 +246,15 @@ def secondary_workloads(dev, stepper, d_img, d_tgt, k=8):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-out', default='')
     ap.add_argument('--no-secondary', action='store_true')
+    ap.add_argument('--no-reference-cuda', action='store_true', help='skip the reference-on-cuDNN secondaries')
+    ap.add_argument('--workload', default='krn', choices=['krn', 'dann'], help='dann = BASELINE.json configs[3] (adapt.py step, 48 source + 48 target images per GPU)')
     ap.add_argument('--dtype', default='fp32', choices=['fp32', 'bf16'], help='bf16 = the --use_fp16 path (secondary number; the headline is fp32)')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -222,8 +265,10 @@ def main():
     from speedplusbaseline_b200 import _lib as L
     from speedplusbaseline_b200 import profiler
     from speedplusbaseline_b200.nets.park2019 import KeypointRegressionNet
+    from speedplusbaseline_b200.nets.revgrad import RevGrad
     from speedplusbaseline_b200.optim import FusedAdamW
-    from speedplusbaseline_b200.core.trainer import KRNTrainStep
+    from speedplusbaseline_b200.core.trainer import KRNTrainStep, DevicePrefetcher
+    from speedplusbaseline_b200.core.dann import DANNTrainStep
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -235,18 +280,30 @@ def main():
         dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=90))
     W = max(3, args.warmup)
     K = max(1, args.steps)
+    dann = args.workload == 'dann'
 
-    model = KeypointRegressionNet(11, device=dev, seed=2021, dtype=L.BF16 if args.dtype == 'bf16' else L.F32)
-    model.train()
-    opt = FusedAdamW(model._store, model.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
-                     clip_mode=1, max_norm=1.0)
-    if world > 1:
-        opt.grad_scale = 1.0 / world
-    stepper = KRNTrainStep(model, opt, use_graph=not args.no_graph, world_size=world)
     g = torch.Generator(device='cpu').manual_seed(2021 + rank)
     h_img = torch.rand(BATCH, 3, HW, HW, generator=g).pin_memory()
     h_tgt = torch.rand(BATCH, 2, 11, generator=g).pin_memory()
-    d_img, d_tgt = h_img.to(dev), h_tgt.to(dev)
+    if dann:
+        model = RevGrad(11, device=dev, seed=2021)
+        h_tim = torch.rand(BATCH, 3, HW, HW, generator=g).pin_memory()          # unlabeled target-domain batch
+        host_batch = (h_img, h_tgt, h_tim)
+    else:
+        model = KeypointRegressionNet(11, device=dev, seed=2021, dtype=L.BF16 if args.dtype == 'bf16' else L.F32)
+        host_batch = (h_img, h_tgt)
+    model.train()
+    opt = FusedAdamW(model._store, model.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
+                     clip_mode=1, max_norm=1.0)
+    if dann:
+        stepper = DANNTrainStep(model, opt, use_graph=not args.no_graph, world_size=world)
+        step = lambda *b: stepper.step(b[0], b[1], b[2], 0.5)
+        eager = lambda *b: stepper.eager(b[0], b[1], b[2], 0.5)
+        per_step = 2 * BATCH
+    else:
+        stepper = KRNTrainStep(model, opt, use_graph=not args.no_graph, world_size=world)
+        step, eager, per_step = stepper.step, stepper.eager, BATCH
+    dev_batch = tuple(t.to(dev) for t in host_batch)
 
     def barrier():
         if world > 1:
@@ -255,12 +312,12 @@ def main():
 
     # launches per step (counted on an eager step; graph replays re-issue the same kernels)
     n0 = L.lib.b200sp_launch_count()
-    stepper.eager(d_img, d_tgt)
+    eager(*dev_batch)
     torch.cuda.synchronize()
     launches_per_step = int(L.lib.b200sp_launch_count() - n0)
 
     for _ in range(W):
-        stepper.step(d_img, d_tgt)
+        step(*dev_batch)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -270,23 +327,22 @@ def main():
     barrier()
     e0.record()
     for _ in range(K):
-        loss3 = stepper.step(d_img, d_tgt)
+        losses = step(*dev_batch)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    loss_after_device_region = float(losses[0])
     # ---- timed region 2: end to end through the public step API with HOST inputs ------------------
-    host_loss = torch.empty(3).pin_memory()
+    nl = int(losses.numel())
+    host_loss = torch.empty(nl).pin_memory()
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    last = None
     # the public loop's input path: pinned host batch -> DevicePrefetcher (H2D of step i+1 on a copy stream while step i
-    # computes) -> KRNTrainStep.step; every step's 28.9 MB H2D and its 12-byte loss D2H are inside the timed region
-    from speedplusbaseline_b200.core.trainer import DevicePrefetcher
-    for di, dt_ in DevicePrefetcher([(h_img, h_tgt)] * K, dev):
-        l3 = stepper.step(di, dt_)
+    # computes) -> stepper.step; every step's H2D and its loss D2H are inside the timed region
+    for db in DevicePrefetcher([host_batch] * K, dev):
+        l3 = step(*db)
         host_loss.copy_(l3, non_blocking=True)
-        last = float(host_loss[0])          # previous step's value unless the copy already landed
     e3.record()
     barrier()
     final_loss = float(host_loss[0])
@@ -298,55 +354,69 @@ def main():
     ms, ms_e2e = float(t[0]), float(t[1])
 
     # per-launch CUDA-event profile of eager steps: every rank runs it (the steps contain the gradient allreduce)
-    prof = profiler.profile_krn_step(stepper, d_img, d_tgt, reps=3)
+    prof = None
+    if not dann:
+        prof = profiler.profile_krn_step(stepper, dev_batch[0], dev_batch[1], reps=3)
     if rank == 0:
         hbm, tf, which = _peaks()
-        value = world * BATCH * K / (ms / 1e3)
-        e2e = world * BATCH * K / (ms_e2e / 1e3)
-        dom = prof['dominant']
-        traffic = None
-        try:
-            tj = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get(dom['name'])
-            if tj:
-                traffic = tj['dram_read'] + tj['dram_write']
-        except Exception:
-            pass
-        roof = {'bound': 'hbm', 'kernel': dom['name'], 'achieved': dom['gbs'], 'peak': hbm, 'unit': 'GB/s',
-                'frac': dom['gbs'] / hbm, 'traffic': traffic, 'peak_source': which + ' (sustained copy)',
-                'share_of_step': dom['share'], 'us_per_launch': dom['us'], 'algorithmic_bytes_per_launch': dom['bytes'],
-                'step_roofline_frac': prof['step_roofline_ms'] / (ms / K),
-                'step_algorithmic_gb': prof['step_bytes'] / 1e9}
-        # the metric's second half, "conv tensor-pipe % of peak" (SURVEY.md §8 d-1): dense conv/FC FLOPs of the reference
-        # graph (2.3345 GFLOP per image for a train step; depthwise excluded, it is CUDA-core work) / step time / measured
-        # dense bf16 peak.  The fp32 path issues 3 tf32 MMAs per product (tf32 rate = bf16/2), so its own ceiling is peak/6.
-        dense_gf = 2.3345 * BATCH
-        tflops = dense_gf / (ms / K)            # GFLOP / ms == TFLOP/s per GPU
-        roof['tensor_pipe'] = {'dense_gflop_per_step': dense_gf, 'achieved': tflops, 'peak': tf, 'unit': 'TFLOP/s',
-                               'frac': tflops / tf, 'peak_source': which + ' (cuBLAS bf16 sustained)',
-                               'mma_per_product': 3 if args.dtype == 'fp32' else 1}
-        if args.profile_out:
-            with open(args.profile_out, 'w') as f:
-                f.write(prof['table'])
+        value = world * per_step * K / (ms / 1e3)
+        e2e = world * per_step * K / (ms_e2e / 1e3)
+        h2d = int(sum(t_.numel() * 4 for t_ in host_batch))
+        if dann:
+            metric, workload = 'dann_adapt_images_per_sec', 'KRN DANN adapt.py step, 48 source + 48 target images per GPU (BASELINE.json configs[3])'
+            math = 'fp32 storage, 3xTF32 tensor-core GEMMs + fp32 CUDA-core stencils (DANN is fp32-only in the reference, adapt.py:99-101)'
+        else:
+            metric, workload = METRIC, 'KRN train bs=48/GPU AdamW 224x224 synthetic (BASELINE.json configs[1])'
+            math = ('fp32 storage, 3xTF32 tensor-core GEMMs + fp32 CUDA-core stencils' if args.dtype == 'fp32' else
+                    'bf16 storage + bf16 tensor-core GEMMs, fp32 accumulate / statistics / master weights')
         line = {
-            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
+            'metric': metric, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': args.dtype, 'data': 'synthetic',
-            'config': {'workload': 'KRN train bs=48/GPU AdamW 224x224 synthetic (BASELINE.json configs[1])',
-                       'math': ('fp32 storage, 3xTF32 tensor-core GEMMs + fp32 CUDA-core stencils' if args.dtype == 'fp32' else
-                                'bf16 storage + bf16 tensor-core GEMMs, fp32 accumulate / statistics / master weights'),
-                       'global_batch': world * BATCH, 'parallelism': 'dp%d' % world,
+            'config': {'workload': workload, 'math': math, 'global_batch': world * per_step, 'parallelism': 'dp%d' % world,
                        'cuda_graph': not args.no_graph,
                        'l2': 'per-step working set ~2.7 GB of activations >> 126 MB L2 (no explicit flush)'},
-            'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(h_img.numel() * 4 + h_tgt.numel() * 4),
-                    'd2h_bytes_per_step': 12, 'ms_per_step': ms_e2e / K},
+            'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4 * nl, 'ms_per_step': ms_e2e / K},
             'gpu_launches': launches_per_step * K, 'launches_per_step': launches_per_step,
-            'clocks': clocks, 'roofline': roof, 'final_loss': final_loss,
+            'clocks': clocks, 'final_loss': final_loss, 'loss_after_device_region': loss_after_device_region,
         }
-        if not args.no_secondary and world == 1:
+        if prof is not None:
+            # roofline of the kernel FAMILY that owns the step (per-family table alongside): algorithmic bytes of all its launches /
+            # the sum of their CUDA-event durations in an eager step, against the measured copy bandwidth.  `traffic` (ncu DRAM
+            # bytes) is not measured inside a bench run: null here, the ncu captures are under profiles/.
+            fams = prof['families']
+            lead = fams[0]
+            roof = {'bound': 'hbm', 'kernel': lead['family'], 'achieved': lead['gbs'], 'peak': hbm, 'unit': 'GB/s',
+                    'frac': lead['gbs'] / hbm, 'traffic': None, 'peak_source': which + ' (sustained copy)',
+                    'share_of_step': lead['share'], 'launches': lead['launches'], 'us_per_step': lead['us'],
+                    'algorithmic_mb_per_step': lead['algorithmic_mb'], 'families': fams,
+                    'longest_launch': prof['dominant'],
+                    'step_roofline_frac': prof['step_roofline_ms'] / (ms / K), 'step_algorithmic_gb': prof['step_bytes'] / 1e9,
+                    'note': 'optimizer family: its 158 MB flat buffers are partly L2-resident after the backward kernels, so its GB/s is not a pure HBM figure'}
+            # the metric's second half, "conv tensor-pipe % of peak" (SURVEY.md 8 d-1): dense conv/FC FLOPs of the reference graph
+            # (2.3345 GFLOP per image for a train step; depthwise excluded) / step time / measured dense bf16 peak.  The fp32 path
+            # issues 3 tf32 MMAs per product (tf32 rate = bf16/2), so its own ceiling is peak/6.
+            dense_gf = 2.3345 * BATCH
+            tflops = dense_gf / (ms / K)
+            roof['tensor_pipe'] = {'dense_gflop_per_step': dense_gf, 'achieved': tflops, 'peak': tf, 'unit': 'TFLOP/s',
+                                   'frac': tflops / tf, 'peak_source': which + ' (cuBLAS bf16 sustained)',
+                                   'mma_per_product': 3 if args.dtype == 'fp32' else 1}
+            line['roofline'] = roof
+            if args.profile_out:
+                with open(args.profile_out, 'w') as f:
+                    f.write(prof['table'])
+        if not args.no_secondary and world == 1 and not dann:
             try:
-                line['secondary'] = secondary_workloads(dev, stepper, d_img, d_tgt)
+                line['secondary'] = secondary_workloads(dev, stepper, dev_batch[0], dev_batch[1])
             except Exception as e:          # secondary numbers never invalidate the headline line
                 line['secondary'] = {'error': repr(e)[:300]}
+            if not args.no_reference_cuda:
+                del stepper
+                torch.cuda.empty_cache()
+                line['secondary'].update(reference_cuda(local))
+                rc = line['secondary'].get('reference_cuda_fp32', {})
+                if 'ms_per_step' in rc:
+                    line['secondary']['speedup_vs_reference_cuda_fp32'] = rc['ms_per_step'] / (ms_e2e / K)
         if not args.no_cpu_baseline and world == 1:
             line['cpu_baseline'] = cpu_baseline()
         print(json.dumps(line))

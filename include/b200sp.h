@@ -108,6 +108,10 @@ int64_t b200sp_launch_count(void);
  * as [MN][Ktot] (reduction contiguous), 1: as [Ktot][MN].  Ktot = nkb * (32 fp32 | 64 bf16). */
 int b200sp_tc_probe(const void *A, const void *B, float *D, int N, int nkb, int mode,
                     int a_major, int b_major, int variant, void *stream);
+/* tcgen05.mma issue-rate probe (mma_probe.cu; measurement tool): `grid` CTAs each issue `iters` back-to-back MMAs (M 128,
+ * K 32 bytes, width N) and write the elapsed clock64 cycles to out_cycles[cta].  kind 0 tf32 | 1 bf16; a_src 0 shared memory
+ * | 1 TMEM; layout 0 SWIZZLE_128B | 1 none | 2 SWIZZLE_64B | 3 SWIZZLE_32B; rotate 1 walks k-steps / stages like a main loop */
+int b200sp_mma_probe(int kind, int a_src, int layout, int N, int iters, int rotate, int grid, long long *out_cycles, void *stream);
 
 /* ---- convolutions -------------------------------------------------------- */
 /* 3x3 stride-2 pad-1 stem, 3 -> Cout(32), NCHW float input (what the loader yields),
@@ -266,6 +270,12 @@ int b200sp_pool_lrn_bwd(const float *g_out, const float *pooled, const float *x,
 /* Dropout(p) (spn.py:81,85,92,96): counter-based mask from `seed` (not torch's RNG stream); mask saved for backward */
 int b200sp_dropout_fwd(const float *x, float *out, uint8_t *mask, int64_t n, float p, uint64_t seed, void *stream);
 int b200sp_dropout_bwd(float *g, const uint8_t *mask, int64_t n, float p, void *stream);
+/* same mask generator with a DEVICE-resident step counter mixed into the seed (int64 *counter, advanced with b200sp_add_i64
+ * once per training forward): the step can be captured in a CUDA graph and still draws a new mask per replay, every
+ * forward of a reference-style loop advances it, and (seed = f(cfg.seed, rank), counter = steps taken) makes masks differ
+ * across ranks and continue after a resume (spn.py:81,85,92,96 use torch's global RNG for the same purpose) */
+int b200sp_dropout_fwd_ctr(const float *x, float *out, uint8_t *mask, int64_t n, float p, uint64_t seed, const int64_t *counter,
+                           void *stream);
 /* softmax_cross_entropy_with_logits (spn.py:37-48): loss_rows[b] = -sum_j t_bj log_softmax(z_b)_j;
  * dlogits (may be NULL) = weight/B * (softmax * sum_j t - t)  (weight: 1 for the class branch, 10 for the regress branch) */
 int b200sp_soft_ce(const float *logits, const float *target, float *loss_rows, float *dlogits, int B, int N, float weight,

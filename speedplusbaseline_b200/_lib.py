@@ -84,6 +84,7 @@ _SIGS = {
     'b200sp_version': ([], i32),
     'b200sp_launch_count': ([], i64),
     'b200sp_tc_probe': ([vp, vp, vp, i32, i32, i32, i32, i32, i32, vp], i32),
+    'b200sp_mma_probe': ([i32, i32, i32, i32, i32, i32, i32, vp, vp], i32),
     'b200sp_stem_fwd': ([vp, vp, vp, PBF, i32, i32, i32, i32, vp], i32),
     'b200sp_stem_wgrad': ([vp, PVT, vp, i32, i32, i32, i32, vp], i32),
     'b200sp_pw_fwd': ([PVT, vp, vp, i32, vp, PBF, i32, i32, i32, i32, vp], i32),
@@ -124,6 +125,7 @@ _SIGS = {
     'b200sp_pool_lrn_bwd': ([vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, i32, vp], i32),
     'b200sp_dropout_fwd': ([vp, vp, vp, i64, f32, C.c_uint64, vp], i32),
     'b200sp_dropout_bwd': ([vp, vp, i64, f32, vp], i32),
+    'b200sp_dropout_fwd_ctr': ([vp, vp, vp, i64, f32, C.c_uint64, vp, vp], i32),
     'b200sp_soft_ce': ([vp, vp, vp, vp, i32, i32, f32, vp], i32),
     'b200sp_soft_ce_mean': ([vp, vp, vp, i32, vp], i32),
     'b200sp_relu_mask': ([vp, vp, i64, vp], i32),

@@ -12,7 +12,9 @@ logger = logging.getLogger(__name__)
 
 
 def select_device(cfg):
-    return torch.device('cuda:0') if torch.cuda.is_available() and cfg.use_cuda else torch.device('cpu')
+    """cuda:0 like the reference (train.py:50); under torchrun one process per GPU on cuda:LOCAL_RANK with an NCCL group."""
+    from .dist import setup_cli
+    return setup_cli(cfg)
 
 
 def setup_logger(name):
@@ -36,7 +38,7 @@ class SyntheticLoader:
 
     def __init__(self, cfg, n, labels=True, seed=0, pin=True):
         self.n, self.labels = n, labels
-        g = torch.Generator().manual_seed(cfg.seed + seed)
+        g = torch.Generator().manual_seed(cfg.seed + seed + 1000 * getattr(cfg, 'rank', 0))     # every rank its own shard
         H, W = cfg.input_shape[0], cfg.input_shape[1]
         self.images = torch.rand(cfg.batch_size, 3, H, W, generator=g)
         self.target = torch.rand(cfg.batch_size, 2, cfg.num_keypoints, generator=g)
@@ -73,7 +75,7 @@ def make_loaders(cfg, specs):
         # those loaders stay with the reference; everything else (KRN train / DANN target / test, SPN test) can decode-only
         if on_device and not (cfg.model_name == 'spn' and s.get('is_train', True)):
             from .datasets.raw import make_dataloader as make_device_dataloader
-            out.append(make_device_dataloader(cfg, device=select_device(cfg), **s))
+            out.append(make_device_dataloader(cfg, device=getattr(cfg, 'device', None) or torch.device('cuda:0'), **s))
         else:
             reference_modules(cfg)
             from src.datasets.build import make_dataloader

@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from .. import _lib as L
-from ..dist import GradSync
+from ..dist import GradSync, world_size
 from ..utils import AverageMeter, report_progress
 
 
@@ -31,7 +31,6 @@ class DANNTrainStep:
             optimizer.grad_scale = self.sync.grad_scale      # 1/world folded into the AdamW kernel
         dev = model.engine.device
         self.neg_alpha = torch.zeros(1, dtype=torch.float32, device=dev)
-        self._alpha_host = torch.zeros(1, dtype=torch.float32).pin_memory()
         self.losses = torch.zeros(3, dtype=torch.float32, device=dev)
         self._graphs = self._static = self._sig = None
 
@@ -56,8 +55,9 @@ class DANNTrainStep:
         self.sync.allreduce(self.model.engine.store.grads)
 
     def _set_alpha(self, alpha):
-        self._alpha_host[0] = -float(alpha)
-        self.neg_alpha.copy_(self._alpha_host, non_blocking=True)
+        # the value travels as a kernel argument of the fill: no reused pinned staging scalar that a later iteration
+        # could overwrite before an earlier asynchronous copy has read it
+        self.neg_alpha.fill_(-float(alpha))
 
     def eager(self, source, label, target, alpha):
         self.opt.sync_hyperparams()
@@ -118,7 +118,7 @@ def train_dann_single_epoch_krn(epoch, cfg, model, dataloader_source, dataloader
     n_batches = min(len(dataloader_source), len(dataloader_target))
     stepper = getattr(model, '_dann_step', None)
     if stepper is None or stepper.opt is not optimizer:
-        stepper = DANNTrainStep(model, optimizer, use_graph=getattr(cfg, 'use_graph', True))
+        stepper = DANNTrainStep(model, optimizer, use_graph=getattr(cfg, 'use_graph', True), world_size=world_size())
         model._dann_step = stepper
     pending = None
     for idx, ((source, label), target) in enumerate(batches):

@@ -13,7 +13,7 @@ import time
 import torch
 
 from .. import _lib as L
-from ..dist import GradSync
+from ..dist import GradSync, world_size
 from ..utils import AverageMeter, report_progress
 
 logger = logging.getLogger("Training")
@@ -60,10 +60,8 @@ class KRNTrainStep:
         self._static[1].copy_(target)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):          # warm-up allocates every activation buffer
+        with torch.cuda.stream(s):          # warm-up allocates every activation buffer (step() snapshots / restores the BN buffers around this)
             cx = self._fwd_bwd(*self._static)
-            # undo the warm-up's side effects on BN running statistics / counters? No: a warm-up
-            # step is a real step for BN buffers; do it on a throw-away copy instead.
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
@@ -106,7 +104,7 @@ def train_single_epoch_krn(epoch, cfg, model, data_loader, optimizer,
         lr = pg['lr']
     stepper = getattr(model, '_train_step', None)
     if stepper is None or stepper.opt is not optimizer:
-        stepper = KRNTrainStep(model, optimizer, use_graph=getattr(cfg, 'use_graph', True))
+        stepper = KRNTrainStep(model, optimizer, use_graph=getattr(cfg, 'use_graph', True), world_size=world_size())
         model._train_step = stepper
     pending = None
     for idx, (images, target) in enumerate(DevicePrefetcher(data_loader, device)):
@@ -209,7 +207,11 @@ class SPNTrainStep:
         if world_size > 1:
             optimizer.grad_scale = self.sync.grad_scale
         self._graphs = self._static = self._sig = None
-        self._step = 0
+        # dropout masks: counter-based generator keyed by (seed, rank) with a DEVICE-resident step counter, so the captured
+        # graph draws a new mask per replay, ranks differ, and a resumed run continues the sequence (engine.drop_ctr)
+        import torch.distributed as dist
+        rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+        self.model.engine.base_seed = (int(getattr(model, 'seed', 0) or 0) * 1000003 + rank) & 0x7fffffff
 
     def _fwd_bwd(self, images, yc, yw):
         eng = self.model.engine
@@ -220,23 +222,20 @@ class SPNTrainStep:
 
     def eager(self, images, yc, yw):
         self.opt.sync_hyperparams()
-        self.model.engine.step_seed = self._step
-        self._step += 1
         out = self._fwd_bwd(images, yc, yw)
         self.sync.allreduce(self.model.engine.store.grads)
         self.opt.step(sync=False)
         return out
 
     def step(self, images, yc, yw):
-        # dropout masks are seeded per step from the host, so the step is replayed eagerly unless dropout is off
-        # (a captured graph would freeze the seed); the launch count is ~110, all asynchronous.
-        if not self.use_graph or self.model.engine.drop_p > 0:
+        if not self.use_graph:
             return self.eager(images, yc, yw)
         sig = tuple(tuple(t.shape) for t in (images, yc, yw))
         if self._graphs is None or sig != self._sig:
             self._static = tuple(torch.empty_like(t) for t in (images, yc, yw))
             for s, t in zip(self._static, (images, yc, yw)):
                 s.copy_(t)
+            ctr = self.model.engine.drop_ctr.clone()
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
@@ -246,6 +245,7 @@ class SPNTrainStep:
             g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(g1):
                 self._fwd_bwd(*self._static)
+            self.model.engine.drop_ctr.copy_(ctr)          # the warm-up pass is not a training step
             with torch.cuda.graph(g2):
                 self.opt.step(sync=False)
             self._graphs, self._sig = (g1, g2), sig
@@ -269,7 +269,7 @@ def train_single_epoch_spn(epoch, cfg, model, data_loader, optimizer,
         lr = pg['lr']
     stepper = getattr(model, '_train_step', None)
     if stepper is None or stepper.opt is not optimizer:
-        stepper = SPNTrainStep(model, optimizer, use_graph=getattr(cfg, 'use_graph', True))
+        stepper = SPNTrainStep(model, optimizer, use_graph=getattr(cfg, 'use_graph', True), world_size=world_size())
         model._train_step = stepper
     pending = None
     for idx, (images, yClasses, yWeights) in enumerate(data_loader):

@@ -174,8 +174,14 @@ __device__ __forceinline__ uint32_t mix32(uint32_t a) {
     return a;
 }
 __global__ void __launch_bounds__(SP_NT) dropout_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, uint8_t* __restrict__ mask,
-                                                           long long n, float p, uint32_t seed_lo, uint32_t seed_hi) {
+                                                           long long n, float p, uint32_t seed_lo, uint32_t seed_hi,
+                                                           const unsigned long long* __restrict__ ctr) {
     const float scale = 1.f / (1.f - p);
+    if (ctr) {            // device-resident step counter: a captured CUDA graph draws a fresh mask on every replay
+        const unsigned long long c = *ctr * 0x9E3779B97F4A7C15ull;
+        seed_lo ^= mix32((uint32_t)c);
+        seed_hi ^= mix32((uint32_t)(c >> 32) + 0x85ebca6bu);
+    }
     for (long long i = (long long)blockIdx.x * SP_NT + threadIdx.x; i < n; i += (long long)gridDim.x * SP_NT) {
         const uint32_t h = mix32((uint32_t)i ^ mix32(seed_lo + 0x9e3779b9u * (uint32_t)(i >> 32)) ^ seed_hi);
         const bool keep = (h >> 8) * (1.f / 16777216.f) >= p;
@@ -288,7 +294,16 @@ extern "C" int b200sp_pool_lrn_bwd(const float* g_out, const float* pooled, cons
 
 extern "C" int b200sp_dropout_fwd(const float* x, float* out, uint8_t* mask, int64_t n, float p, uint64_t seed, void* stream) {
     if (p < 0.f || p >= 1.f) return B200SP_EINVAL;
-    dropout_fwd_kernel<<<sp_grid(n), SP_NT, 0, (cudaStream_t)stream>>>(x, out, mask, n, p, (uint32_t)seed, (uint32_t)(seed >> 32));
+    dropout_fwd_kernel<<<sp_grid(n), SP_NT, 0, (cudaStream_t)stream>>>(x, out, mask, n, p, (uint32_t)seed, (uint32_t)(seed >> 32), nullptr);
+    B200SP_COUNT_LAUNCH();
+    B200SP_RETURN_LAST();
+}
+
+extern "C" int b200sp_dropout_fwd_ctr(const float* x, float* out, uint8_t* mask, int64_t n, float p, uint64_t seed, const int64_t* counter,
+                                      void* stream) {
+    if (p < 0.f || p >= 1.f || !counter) return B200SP_EINVAL;
+    dropout_fwd_kernel<<<sp_grid(n), SP_NT, 0, (cudaStream_t)stream>>>(x, out, mask, n, p, (uint32_t)seed, (uint32_t)(seed >> 32),
+                                                                      reinterpret_cast<const unsigned long long*>(counter));
     B200SP_COUNT_LAUNCH();
     B200SP_RETURN_LAST();
 }

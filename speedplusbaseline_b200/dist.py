@@ -60,3 +60,52 @@ def shard(t, rank, world):
     """contiguous batch shard of a global-batch tensor (per-GPU batch = global / world)."""
     n = t.shape[0] // world
     return t[rank * n:(rank + 1) * n]
+
+
+def world_size():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def rank():
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def setup_cli(cfg):
+    """Device + process group for train.py / adapt.py / test.py.  Single process: the reference's own rule
+    (cuda:0 when available and not --no_cuda, train.py:50).  Under torchrun (WORLD_SIZE > 1): one process per GPU,
+    cuda:LOCAL_RANK, NCCL process group; `cfg.device` tells get_model where to build the engine."""
+    r, world, local = env_world()
+    use_cuda = torch.cuda.is_available() and cfg.use_cuda
+    if world > 1:
+        if use_cuda:
+            torch.cuda.set_device(local)
+            device = torch.device('cuda', local)
+            init_process_group('nccl', device)
+        else:
+            device = torch.device('cpu')
+            init_process_group('gloo')
+    else:
+        device = torch.device('cuda:0') if use_cuda else torch.device('cpu')
+    cfg.device = device if device.type == 'cuda' else None
+    cfg.rank, cfg.world_size = r, world
+    return device
+
+
+def broadcast_model(model):
+    """Replicas must start from identical parameters / BN buffers (every rank constructs its model with its own RNG
+    state): rank 0's flat buffers are broadcast once.  No-op for a single process."""
+    if world_size() <= 1:
+        return
+    st = getattr(model, '_store', None)
+    if st is not None:
+        for t in (st.params, st.bufs, st.nbt):
+            dist.broadcast(t, 0)
+        if getattr(st, 'params_lowp', None) is not None:
+            st.params_lowp.copy_(st.params)
+    else:
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t.data, 0)
+
+
+def is_main():
+    return rank() == 0

@@ -154,13 +154,33 @@ def _summarise(best, reps):
     top = sorted(best, key=lambda r: -r[2])[:25]
     for n, b, t, tag in top:
         lines.append('%-24s %10.1f us %10.2f MB %9.1f GB/s   [%s]' % (n, t, b / 1e6, b / 1e3 / max(t, 1e-3), tag))
-    # dominant kernel = the single launch configuration with the largest time
     n, b, t, tag = top[0]
     hbm = 6545.9
     p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'MEASURED_PEAKS.json')
     if os.path.exists(p):
         hbm = json.load(open(p)).get('hbm_gbs', hbm)
+    # kernel FAMILIES: the three pointwise-GEMM entry points are one kernel family (tcgemm2.cu / tcgemm.cu), the two depthwise
+    # entry points another (dwroll.cu); the roofline object of the bench line leads with the family that owns the step
+    groups = OrderedDict((('pointwise_gemm', ('b200sp_pw_fwd', 'b200sp_pw_dgrad', 'b200sp_pw_wgrad')),
+                          ('depthwise', ('b200sp_dw_fwd', 'b200sp_dw_bwd')),
+                          ('stem', ('b200sp_stem_fwd', 'b200sp_stem_wgrad')),
+                          ('optimizer', ('b200sp_adamw_step', 'b200sp_grad_sqnorm', 'b200sp_optim_step'))))
+    fams, seen = [], set()
+    for gname, members in groups.items():
+        c = sum(agg[m][0] for m in members if m in agg)
+        t_ = sum(agg[m][1] for m in members if m in agg)
+        b_ = sum(agg[m][2] for m in members if m in agg)
+        seen.update(members)
+        if c:
+            fams.append({'family': gname, 'launches': c, 'us': t_, 'share': t_ / total, 'algorithmic_mb': b_ / 1e6,
+                         'gbs': b_ / 1e3 / max(t_, 1e-3), 'frac_of_hbm_peak': b_ / 1e3 / max(t_, 1e-3) / hbm})
+    c = sum(v[0] for k, v in agg.items() if k not in seen)
+    t_ = sum(v[1] for k, v in agg.items() if k not in seen)
+    b_ = sum(v[2] for k, v in agg.items() if k not in seen)
+    fams.append({'family': 'other (bn_apply, head, reorg, loss)', 'launches': c, 'us': t_, 'share': t_ / total, 'algorithmic_mb': b_ / 1e6,
+                 'gbs': b_ / 1e3 / max(t_, 1e-3), 'frac_of_hbm_peak': b_ / 1e3 / max(t_, 1e-3) / hbm})
+    fams.sort(key=lambda f: -f['us'])
     return {'table': '\n'.join(lines) + '\n', 'step_bytes': step_bytes, 'step_roofline_ms': step_bytes / hbm / 1e6,
-            'eager_kernel_ms': total / 1e3,
+            'eager_kernel_ms': total / 1e3, 'families': fams,
             'dominant': {'name': '%s[%s]' % (n, tag), 'us': t, 'bytes': b, 'gbs': b / 1e3 / max(t, 1e-3),
                          'share': t / total}}

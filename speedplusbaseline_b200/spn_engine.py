@@ -47,7 +47,8 @@ class SPNEngine:
         self._bufs = {}
         self.keep = []
         self.drop_p = 0.5
-        self.step_seed = 0
+        self.base_seed = 0                 # f(cfg.seed, rank): set by the training step / CLI
+        self.drop_ctr = torch.zeros(1, dtype=torch.int64, device=self.device)     # training forwards taken (device-resident)
 
     def _buf(self, name, shape, dtype=torch.float32):
         t = self._bufs.get(name)
@@ -170,6 +171,8 @@ class SPNEngine:
         self._dcol_elems = max(B * H2 * W2 * 1200, B * H3 * W3 * 2304)
         drop = train and self.drop_p > 0
         self.drop = drop
+        if drop:               # one tick per training forward: every forward (eager, module facade or graph replay) draws new masks
+            L.call('b200sp_add_i64', self.drop_ctr.data_ptr(), 1, 1, L.stream_ptr())
         out = []
         for bi, (fa, fb, fc) in enumerate((('fc6', 'fc7', 'fc8'), ('fc9', 'fc10', 'fc11'))):
             h1 = self._fc_fwd(fa, f, B, 9216, 4096, L.ACT_RELU, fa)
@@ -192,8 +195,9 @@ class SPNEngine:
     def _dropout(self, h, tag, idx):
         out = self._buf('hd_' + tag, tuple(h.shape))
         mask = self._buf('m_' + tag, tuple(h.shape), torch.uint8)
-        seed = (self.step_seed * 4 + idx) * 0x9E3779B97F4A7C15 & 0xFFFFFFFFFFFFFFFF
-        L.call('b200sp_dropout_fwd', h.data_ptr(), out.data_ptr(), mask.data_ptr(), h.numel(), float(self.drop_p), seed, L.stream_ptr())
+        seed = ((self.base_seed * 4 + idx + 1) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        L.call('b200sp_dropout_fwd_ctr', h.data_ptr(), out.data_ptr(), mask.data_ptr(), h.numel(), float(self.drop_p), seed,
+               self.drop_ctr.data_ptr(), L.stream_ptr())
         return out
 
     # ------------------------------------------------------------------ backward

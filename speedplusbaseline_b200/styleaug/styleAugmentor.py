@@ -4,8 +4,8 @@ sampled exactly like the reference (CPU `torch.randn(n,100)` -> same RNG stream 
 styleAugmentor.py:47), everything after that is libb200sp kernels (ghiasi.GhiasiEngine).
 
 Checkpoints (Ghiasi weights, PBN embedding mean/covariance, SPEED+ mean embedding) are the reference's own
-files src/styleaug/checkpoints/*; they are looked up in $SPEEDPLUS_STYLE_CKPT, <repo>/baseline/_ref/
-styleaug_checkpoints, then $SPEEDPLUS_REFERENCE/src/styleaug/checkpoints."""
+files src/styleaug/checkpoints/*; they are looked up in $SPEEDPLUS_STYLE_CKPT, the staged reference
+<repo>/baseline/_ref/src/styleaug/checkpoints (tools/stage_reference.py), then $SPEEDPLUS_REFERENCE/src/styleaug/checkpoints."""
 import os
 
 import numpy as np
@@ -19,7 +19,8 @@ _ROOT = os.path.dirname(os.path.dirname(_HERE))
 
 
 def checkpoint_dir():
-    cands = [os.environ.get('SPEEDPLUS_STYLE_CKPT', ''), os.path.join(_ROOT, 'baseline', '_ref', 'styleaug_checkpoints'),
+    cands = [os.environ.get('SPEEDPLUS_STYLE_CKPT', ''), os.path.join(_ROOT, 'baseline', '_ref', 'src', 'styleaug', 'checkpoints'),
+             os.path.join(_ROOT, 'baseline', '_ref', 'styleaug_checkpoints'),
              os.path.join(os.environ.get('SPEEDPLUS_REFERENCE', ''), 'src', 'styleaug', 'checkpoints'),
              os.path.join(_HERE, 'checkpoints')]
     for c in cands:
@@ -53,17 +54,18 @@ class StyleAugmentor(torch.nn.Module):
         self.A = A.float().contiguous().to(self.device)                       # 100 x 100
         self.mean = state['mean'].float().reshape(-1).contiguous().to(self.device)
         self.imagenet_embedding = state['base'].float().reshape(-1).contiguous().to(self.device)   # SPEED+ mean, despite the name
-        self._noise_host = None
         self.use_graph = use_graph
         self._graph = None            # (shape, graph, static x, static noise, static out)
 
     def sample_noise(self, n):
         """the reference draws on the CPU generator (styleAugmentor.py:47): same stream under torch.manual_seed"""
         noise = torch.randn(n, 100)
-        if self._noise_host is None or self._noise_host.shape[0] != n:
-            self._noise_host = torch.empty(n, 100).pin_memory()
-        self._noise_host.copy_(noise)
-        return self._noise_host.to(self.device, non_blocking=True)
+        # a FRESH pinned buffer per call (torch's caching host allocator recycles it only after the copy that uses it has
+        # completed on its stream): a single reused staging buffer could be overwritten by the next call's draw while the
+        # previous asynchronous H2D copy is still queued
+        host = torch.empty(n, 100, pin_memory=True)
+        host.copy_(noise)
+        return host.to(self.device, non_blocking=True)
 
     def embed(self, noise):
         B = noise.shape[0]

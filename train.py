@@ -16,15 +16,16 @@ logger = logging.getLogger(__name__)
 def main():
     from speedplusbaseline_b200 import cli
     from speedplusbaseline_b200.utils import set_all_seeds, save_checkpoint
+    from speedplusbaseline_b200 import dist as D
     device = cli.select_device(cfg)
     cli.setup_logger('train')
     logger.info('Random seed value: {}'.format(cfg.seed))
-    set_all_seeds(cfg.seed, cfg, True)
+    set_all_seeds(cfg.seed + D.rank(), cfg, True)       # per-rank RNG streams (data order, style noise); weights are broadcast below
     os.makedirs(cfg.savedir, exist_ok=True)
     os.makedirs(cfg.logdir, exist_ok=True)
     try:
         from torch.utils.tensorboard import SummaryWriter
-        writer = SummaryWriter(cfg.logdir)
+        writer = SummaryWriter(cfg.logdir) if D.is_main() else None
     except Exception:                                   # tensorboard not installed: keep training
         writer = None
     with open(os.path.join(cfg.savedir, 'config.txt'), 'w') as f:
@@ -41,6 +42,7 @@ def main():
         from src.styleaug.styleAugmentor import StyleAugmentor
 
     model = get_model(cfg)
+    D.broadcast_model(model)
     styleAugmentor = None
     if cfg.randomize_texture:
         styleAugmentor = StyleAugmentor(cfg.texture_alpha, device)
@@ -67,10 +69,15 @@ def main():
         perf = epoch + 1
         is_best = perf > best_perf
         best_perf = max(best_perf, perf)
+        if not D.is_main():                          # replicas are identical after every step: rank 0 writes the checkpoint
+            continue
         save_checkpoint({'epoch': epoch + 1, 'model': cfg.model_name, 'state_dict': model.state_dict(),
                          'best_score': best_perf, 'optimizer': optimizer.state_dict()}, is_best, cfg.savedir)
     if writer is not None:
         writer.close()
+    if D.world_size() > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == '__main__':
