@@ -102,11 +102,11 @@ __global__ void __launch_bounds__(CT_NT, 1) convtc_kernel(const __grid_constant_
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);      // broadcast form: TMEM addresses stay in uniform registers
 
     if (warp == 0) {
         // ===================================== TMA PRODUCER =====================================
-        if (lane == 0) {
+        if (tc::elect_one()) {       // elect.sync: the TMA / MMA issue below compiles without per-instruction waterfall loops
             int s = 0;
             uint32_t par = 1;
             const uint32_t tx = CT_A_BYTES + (uint32_t)BN * 128u;
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(CT_NT, 1) convtc_kernel(const __grid_constant_
             for (int j = 0; j < g.n_chunks; ++j) {
                 ct_wait(&full[s], par);
                 tc::tc_fence_after();
-                if (lane == 0) {
+                if (tc::elect_one()) {
                     const uint32_t a_s = s_base + s * g.stage_bytes, b_s = a_s + CT_A_BYTES;
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)

@@ -19,6 +19,15 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one elected lane of a fully active warp (elect.sync): ptxas knows exactly one lane passes, so uniform-datapath instructions
+// (tcgen05.mma / commit, TMA) inside `if (elect_one())` are issued straight from uniform registers instead of being wrapped in
+// a per-instruction "elect + loop while any lane remains" waterfall, which is what `if (lane == 0)` compiles to
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- mbarrier -----------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);      // broadcast form: TMEM addresses stay in uniform registers
     // operand tile offsets inside one ring stage (A only when B is resident)
     const uint32_t b_in_stage = E::NM * g.a_op_bytes;
 
@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
                 mbar_wait_guard(&full[os], fpar, g.wait_mode);
                 tc::tc_fence_after();
                 if (lane == 0) TL(5, tlm);
-                if (lane == 0) {
+                if (tc::elect_one()) {
                     const uint32_t a_hi = s_base + os * g.op_stage_bytes, a_lo = a_hi + g.a_op_bytes;
                     const uint32_t b_hi = g.b_res ? s_base + g.off_bres + kb * (E::NM * g.b_op_bytes) : a_hi + b_in_stage;
                     const uint32_t b_lo = b_hi + g.b_op_bytes;

@@ -73,6 +73,12 @@ struct alignas(64) Tcg2Args {
 };
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_T) : "memory"); }
+// Waiting on an mbarrier costs issue slots: try_wait's suspend window is short and ends on any barrier activity, so a waiting warp
+// re-polls continuously (r2c ncu capture of the long-M forward: 62 % of ALL executed warp-instructions were the 16 converter
+// warps polling `empty`).  Hence ONE warp per role polls and releases the others through a hardware named barrier, on
+// which waiting warps issue nothing.
+__device__ __forceinline__ void conv_bar() { asm volatile("bar.sync 2, %0;" ::"n"(PROD_T) : "memory"); }
+__device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // bounded waits: a protocol bug traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t parity, int mode = 0) {
@@ -288,13 +294,13 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);      // broadcast form: keeps the TMEM address (and everything derived from it) in UNIFORM registers, so tcgen05.mma needs no per-instruction R2UR waterfall
     const uint32_t b_in_stage = E::NM * g.a_op_bytes;
     constexpr int slotA2 = APT, slotB = AMODE == XM_DY ? 2 * APT : APT;     // 8192-byte sub-slots of a raw stage: A | [A2] | B
 
     if (warp == TMA_WARP) {
         // ======================================= TMA PRODUCER =====================================
-        if (lane == 0) {
+        if (tc::elect_one()) {
             int rs = 0;
             uint32_t par = 1;
             if (g.b_res) {
@@ -333,7 +339,9 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
         if (g.b_res) {
             for (int kb = 0; kb < g.nkb; ++kb) {
                 CB.load_params(kb);
-                mbar_wait_guard(&rawfull[rs], rpar);
+                if (warp == TMA_WARP + 1) mbar_wait_guard(&rawfull[rs], rpar);
+                conv_bar();
+                tc::mbar_try_wait(&rawfull[rs], rpar);          // completes at once: every thread observes the TMA phase itself
                 const uint32_t b_hi = s_base + g.off_bres + kb * (E::NM * g.b_op_bytes), b_lo = b_hi + g.b_op_bytes;
                 CB.convert(kb, 0, raw0 + rs * g.raw_stage_bytes, 0, b_hi, b_lo);
                 __syncwarp();
@@ -351,8 +359,12 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
         while (cons.valid()) {
             CA.load_params(cons.kb);
             if (!g.b_res) CB.load_params(cons.kb);
-            mbar_wait_guard(&rawfull[rs], rpar);
-            mbar_wait_guard(&empty[os], opar);
+            if (warp == TMA_WARP + 1) {
+                mbar_wait_guard(&rawfull[rs], rpar);
+                mbar_wait_guard(&empty[os], opar);
+            }
+            conv_bar();
+            tc::mbar_try_wait(&rawfull[rs], rpar);              // completes at once: every thread observes the TMA phase itself
             const uint32_t rbase = raw0 + rs * g.raw_stage_bytes;
             const uint32_t a_hi = s_base + os * g.op_stage_bytes, a_lo = a_hi + g.a_op_bytes;
             const uint32_t b_hi = a_hi + b_in_stage, b_lo = b_hi + g.b_op_bytes;
@@ -393,11 +405,9 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
             // ulp of bias; keeping the small terms out of it cuts the number of such truncations from 3K/8 to K/8.
             const uint32_t d_corr = d_tmem + (g.acc_cols > g.BN ? g.BN : 0);
             for (int kb = w.kb0; kb < w.kb1; ++kb) {
-                if (lane == 0) TL(4, tlm);
                 mbar_wait_guard(&full[os], fpar, g.wait_mode);
                 tc::tc_fence_after();
-                if (lane == 0) TL(5, tlm);
-                if (lane == 0) {
+                if (tc::elect_one()) {
                     const uint32_t a_hi = s_base + os * g.op_stage_bytes, a_lo = a_hi + g.a_op_bytes;
                     const uint32_t b_hi = g.b_res ? s_base + g.off_bres + kb * (E::NM * g.b_op_bytes) : a_hi + b_in_stage;
                     const uint32_t b_lo = b_hi + g.b_op_bytes;
@@ -475,7 +485,11 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
             const Item w = get_item(g, it);
             if (do_stats && cur_q0 >= 0 && cur_q0 != w.q0) flush(cur_q0);
             cur_q0 = w.q0;
-            mbar_wait_sleep(&tfull[acc], tpar, g.epi_sleep);
+            {   // one polling warp per epilogue set, the others wait on a named barrier (ids 3 / 4)
+                const int set = g.split_epi ? half : 0;
+                if ((warp & 3) == 0 && (g.split_epi || warp == 0)) mbar_wait_sleep(&tfull[acc], tpar, g.epi_sleep);
+                named_bar(3 + set, g.split_epi ? 128 : EPI_T);
+            }
             tc::tc_fence_after();
             const uint32_t t_row = tmem_base + acc * g.acc_cols + ((uint32_t)(lq * 32) << 16);
             const bool split_acc = g.acc_cols > g.BN;
