@@ -25,7 +25,12 @@
 #include "tc_common.cuh"
 #include "tma.cuh"
 
+#ifdef TCG_TIMELINE          // debug build (B200SP_LIB_SUFFIX=_tl B200SP_NVCC_EXTRA=-DTCG_TIMELINE): clock64 stamps of CTA 0, tools/tcg2_timeline.py
+__device__ long long g_tcg2_tl[11][512];
+#define TL(row, idx) do { if (blockIdx.x == 0 && (idx) < 512) g_tcg2_tl[row][idx] = clock64(); } while (0)
+#else
 #define TL(row, idx) do {} while (0)
+#endif
 
 namespace {
 
@@ -39,7 +44,7 @@ constexpr int PROD_TID0 = EPI_T + MMA_T + TMA_T;
 constexpr int NT = EPI_T + MMA_T + TMA_T + PROD_T;     // 832 threads
 constexpr int BM = 128;
 constexpr int STG_LD = 36;
-constexpr int MAX_OP = 4, MAX_RAW = 6;
+constexpr int MAX_OP = 4, MAX_RAW = 8;
 
 struct ETf { static constexpr int ES = 4, KE = 32, EPV = 4, NM = 2; static constexpr bool TF32 = true; };
 
@@ -48,7 +53,7 @@ struct alignas(64) Tcg2Args {
     b200sp_vtensor a, b;
     int P, Q, R, lda, ldb, ldo;
     int BN, numPt, numQt, splits, kb_per_split, nkb;
-    int n_op, n_raw;
+    int n_op, n_raw, groups;
     int b_res;
     int ac_last, nks_last;
     int b_atoms;                     // MN-major B: 128-byte atoms per tile
@@ -77,7 +82,6 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"
 // re-polls continuously (r2c ncu capture of the long-M forward: 62 % of ALL executed warp-instructions were the 16 converter
 // warps polling `empty`).  Hence ONE warp per role polls and releases the others through a hardware named barrier, on
 // which waiting warps issue nothing.
-__device__ __forceinline__ void conv_bar() { asm volatile("bar.sync 2, %0;" ::"n"(PROD_T) : "memory"); }
 __device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // bounded waits: a protocol bug traps instead of hanging the GPU
@@ -168,37 +172,33 @@ __device__ __forceinline__ void split_store(float4 v, uint32_t dst_hi, uint32_t 
 }
 
 // ---- converter: one thread's share of an operand tile ---------------------------------------------------
-// The raw stage holds the TMA boxes densely, which is exactly "piece i of thread pt at pt*16 + i*8192":
-//   K-major : piece = 16-byte chunk gc = pt & 7 of row (pt >> 3) + 64 i                  (box {32 floats, rows})
-//   MN-major: piece = chunk gc of reduction row (pt >> 3) & 31 of atom 2i + (pt >> 8)    (one {32, 32} box per atom, 4096 B apart)
-// and the operand tile uses the same (row, chunk) with the UMMA swizzle applied to the chunk index.
+// The raw stage holds the TMA boxes densely: 16-byte piece q of an operand lives at byte q*16, and
+//   K-major : q = row*8 + chunk                       (box {32 floats, rows})
+//   MN-major: q = atom*256 + row*8 + chunk            (one {32 floats, 32 reduction rows} box per 128-byte atom)
+// The operand tile uses the same (atom, row, chunk) with the UMMA swizzle applied to the chunk index.  A converter GROUP of
+// GT threads (GT = 512 / groups, a multiple of 128) deals the pieces q = pg + i*GT: the chunk index and the swizzle phase of
+// a thread's pieces never change (GT/8 rows is a multiple of 8), so source and destination both advance by GT*16 bytes.
 template <int LAY, int MODE>
 struct Conv {
     b200sp_vtensor vt;
     ActP act;
     int R, nkb, ac_last, mn_ext;
-    int gc, row, abase, np;
+    int gc, pg, GT, npieces;
     uint32_t soff;
     XfP par;
-    __device__ __forceinline__ void init(const b200sp_vtensor& t, int mn_ext_, int R_, int nkb_, int ac_last_, int pt, int tile_rows) {
+    __device__ __forceinline__ void init(const b200sp_vtensor& t, int mn_ext_, int R_, int nkb_, int ac_last_, int pg_, int GT_, int tile_rows) {
         vt = t; act = act_params(t.act);
         R = R_; nkb = nkb_; ac_last = ac_last_; mn_ext = mn_ext_;
-        gc = pt & 7;
+        pg = pg_; GT = GT_;
+        gc = pg & 7;
         if (LAY == TCG_LAY_KM) {
-            row = pt >> 3; abase = 0;
-            soff = tc::sw128_off(row, gc);
-            const int rem = tile_rows - row;
-            np = rem <= 0 ? 0 : (rem + 63) >> 6;
+            soff = tc::sw128_off(pg >> 3, gc);
+            npieces = tile_rows * 8;
         } else {
-            const int atoms = (tile_rows * 4 + 127) / 128;
-            row = (pt >> 3) & 31; abase = pt >> 8;
-            soff = tc::sw128b32_off(row, gc) + abase * 4096;
-            np = (atoms - abase + 1) >> 1;
+            soff = (uint32_t)(pg >> 8) * 4096u + tc::sw128b32_off((pg >> 3) & 31, gc);
+            npieces = ((tile_rows * 4 + 127) / 128) * 256;
         }
-        if (np > APT) np = APT;
-        if (np < 0) np = 0;
     }
-    // K-major: the transform parameters of k-block kb (channel = reduction index); issue early, the latency hides behind the waits
     __device__ __forceinline__ void load_params(int kb) {
         if (LAY == TCG_LAY_KM && MODE != XM_PLAIN) {
             int ch = kb * 32 + gc * 4;
@@ -206,37 +206,36 @@ struct Conv {
             xf_load<MODE>(vt, ch, par);
         }
     }
-    // raw / raw2: this thread's piece 0 in the raw stage (stage base + operand offset + pt*16); op_hi / op_lo: operand tile bases
+    // raw / raw2: this thread's piece 0 in the raw stage (stage base + operand offset + pg*16); op_hi / op_lo: operand tile bases
     __device__ __forceinline__ void convert(int kb, int mn0, uint32_t raw, uint32_t raw2, uint32_t op_hi, uint32_t op_lo) {
+        const uint32_t step = (uint32_t)GT * 16u;
         if (LAY == TCG_LAY_KM) {
             if (kb == nkb - 1 && gc >= ac_last) return;           // partial last k-block: the MMA never reads these chunks
-#pragma unroll
-            for (int i = 0; i < APT; ++i) {
-                if (i < np) {
-                    const float4 r = lds4(raw + i * 8192);
-                    float4 r2 = f4zero();
-                    if (MODE == XM_DY) r2 = lds4(raw2 + i * 8192);
-                    split_store(xf_apply<MODE>(r, r2, par, act), op_hi + soff + i * 8192, op_lo + soff + i * 8192);
-                }
+            uint32_t o = 0;
+#pragma unroll 2
+            for (int q = pg; q < npieces; q += GT, o += step) {
+                const float4 r = lds4(raw + o);
+                float4 r2 = f4zero();
+                if (MODE == XM_DY) r2 = lds4(raw2 + o);
+                split_store(xf_apply<MODE>(r, r2, par, act), op_hi + soff + o, op_lo + soff + o);
             }
         } else {
-            // reduction rows beyond R were zero-filled by the TMA unit, but a transformed zero is not zero: mask them
-            const bool rok = MODE == XM_PLAIN || kb * 32 + row < R;
-#pragma unroll
-            for (int i = 0; i < APT; ++i) {
-                if (i < np) {
-                    const float4 r = lds4(raw + i * 8192);
-                    float4 r2 = f4zero();
-                    if (MODE == XM_DY) r2 = lds4(raw2 + i * 8192);
-                    if (MODE != XM_PLAIN) {
-                        int ch = mn0 + (2 * i + abase) * 32 + gc * 4;
-                        ch = min(ch, mn_ext - 4);
-                        xf_load<MODE>(vt, ch, par);
-                    }
-                    float4 v = xf_apply<MODE>(r, r2, par, act);
-                    if (!rok) v = f4zero();
-                    split_store(v, op_hi + soff + i * 8192, op_lo + soff + i * 8192);
+            uint32_t o = 0;
+#pragma unroll 2
+            for (int q = pg; q < npieces; q += GT, o += step) {
+                const float4 r = lds4(raw + o);
+                float4 r2 = f4zero();
+                if (MODE == XM_DY) r2 = lds4(raw2 + o);
+                float4 v = r;
+                if (MODE != XM_PLAIN) {
+                    int ch = mn0 + (q >> 8) * 32 + gc * 4;
+                    ch = min(ch, mn_ext - 4);
+                    xf_load<MODE>(vt, ch, par);
+                    v = xf_apply<MODE>(r, r2, par, act);
+                    // reduction rows beyond R were zero-filled by the TMA unit, but a transformed zero is not zero: mask them
+                    if (kb * 32 + ((q >> 3) & 31) >= R) v = f4zero();
                 }
+                split_store(v, op_hi + soff + o, op_lo + soff + o);
             }
         }
     }
@@ -275,10 +274,11 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
     const int total = g.numPt * g.numQt * g.splits;
 
     if (tid == 0) {
-        for (int i = 0; i < MAX_OP; ++i) { tc::mbar_init(&full[i], PROD_T / 32); tc::mbar_init(&empty[i], 1); }
+        const int gw = PROD_T / 32 / g.groups;                 // warps per converter group
+        for (int i = 0; i < MAX_OP; ++i) { tc::mbar_init(&full[i], gw); tc::mbar_init(&empty[i], 1); }
         for (int i = 0; i < 4; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], g.split_epi ? EPI_W / EPI_SETS : EPI_W); }
         tc::mbar_init(bfull, PROD_T / 32);
-        for (int i = 0; i < MAX_RAW; ++i) { tc::mbar_init(&rawfull[i], 1); tc::mbar_init(&rawempty[i], PROD_T / 32); }
+        for (int i = 0; i < MAX_RAW; ++i) { tc::mbar_init(&rawfull[i], 1); tc::mbar_init(&rawempty[i], gw); }
         tc::mbar_fence_init();
     }
     if (warp == TMA_WARP && lane == 0) {
@@ -314,8 +314,12 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
             const uint32_t tx = g.a_tx * (AMODE == XM_DY ? 2u : 1u) + (g.b_res ? 0u : g.b_tx);
             KIter f;
             f.init(g, blockIdx.x, total, gridDim.x);
+            int tlt = 0;
             while (f.valid()) {
+                TL(0, tlt);
                 mbar_wait_guard(&rawempty[rs], par);
+                TL(1, tlt);
+                ++tlt;
                 const uint32_t rbase = s_base + g.off_raw + rs * g.raw_stage_bytes;
                 const uint32_t bar = tc::smem_u32(&rawfull[rs]);
                 tc::mbar_arrive_expect_tx(&rawfull[rs], tx);
@@ -328,42 +332,55 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
         }
     } else if (warp > TMA_WARP) {
         // ======================================= CONVERTERS =======================================
+        // `groups` converter groups of GT = 512/groups threads; group gi owns the k-block sequence numbers n = gi (mod groups) of
+        // this CTA's stream [resident-B k-blocks | (tile, k-block) items] -- several k-blocks are in conversion at once, which is
+        // what hides the lds -> ALU -> sts -> proxy fence -> arrive latency chain (~1300 cycles per k-block, r2f timelines).
+        // n_raw and n_op are multiples of `groups`, so a ring slot is always filled by the same group (single-producer phases).
         const int pt = tid - PROD_TID0;
+        const int G = g.groups, GT = PROD_T / G;
+        const int gi = pt / GT, pg = pt - gi * GT;
+        const bool poller = (pg >> 5) == 0;                      // first warp of the group polls the mbarriers
         Conv<ALAY, AMODE> CA;
         Conv<BLAY, BMODE> CB;
-        CA.init(g.a, g.P, g.R, g.nkb, g.ac_last, pt, BM);
-        CB.init(g.b, g.Q, g.R, g.nkb, g.ac_last, pt, g.BN);
-        const uint32_t raw0 = s_base + g.off_raw + pt * 16;
-        int rs = 0;
-        uint32_t rpar = 0;
+        CA.init(g.a, g.P, g.R, g.nkb, g.ac_last, pg, GT, BM);
+        CB.init(g.b, g.Q, g.R, g.nkb, g.ac_last, pg, GT, g.BN);
+        const uint32_t raw0 = s_base + g.off_raw + pg * 16;
+        int n = gi;                                              // sequence number of the k-block this group converts next
+        const int nb = g.b_res ? g.nkb : 0;
+        for (; n < nb; n += G) {
+            const int rs = n % g.n_raw;
+            const uint32_t rpar = (uint32_t)(n / g.n_raw) & 1u;
+            if (poller) mbar_wait_guard(&rawfull[rs], rpar);
+            named_bar(2 + gi, GT);
+            tc::mbar_try_wait(&rawfull[rs], rpar);              // completes at once: every thread observes the TMA phase itself
+            const uint32_t b_hi = s_base + g.off_bres + n * (E::NM * g.b_op_bytes), b_lo = b_hi + g.b_op_bytes;
+            CB.load_params(n);
+            CB.convert(n, 0, raw0 + rs * g.raw_stage_bytes, 0, b_hi, b_lo);
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&rawempty[rs]);
+        }
         if (g.b_res) {
-            for (int kb = 0; kb < g.nkb; ++kb) {
-                CB.load_params(kb);
-                if (warp == TMA_WARP + 1) mbar_wait_guard(&rawfull[rs], rpar);
-                conv_bar();
-                tc::mbar_try_wait(&rawfull[rs], rpar);          // completes at once: every thread observes the TMA phase itself
-                const uint32_t b_hi = s_base + g.off_bres + kb * (E::NM * g.b_op_bytes), b_lo = b_hi + g.b_op_bytes;
-                CB.convert(kb, 0, raw0 + rs * g.raw_stage_bytes, 0, b_hi, b_lo);
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&rawempty[rs]);
-                if (++rs == g.n_raw) { rs = 0; rpar ^= 1; }
-            }
             tc::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(bfull);
         }
         KIter cons;
         cons.init(g, blockIdx.x, total, gridDim.x);
-        int os = 0;
-        uint32_t opar = 1;
+        for (int sk = nb; sk < n && cons.valid(); ++sk) cons.next(g);       // this group's first item
+        int tlc = 0;
         while (cons.valid()) {
+            const int rs = n % g.n_raw, m = n - nb, os = m % g.n_op;
+            const uint32_t rpar = (uint32_t)(n / g.n_raw) & 1u, opar = ((uint32_t)(m / g.n_op) & 1u) ^ 1u;
             CA.load_params(cons.kb);
             if (!g.b_res) CB.load_params(cons.kb);
-            if (warp == TMA_WARP + 1) {
+            if (pt == 0) TL(2, tlc);
+            if (poller) {
                 mbar_wait_guard(&rawfull[rs], rpar);
+                if (pt == 0) TL(3, tlc);
                 mbar_wait_guard(&empty[os], opar);
+                if (pt == 0) TL(4, tlc);
             }
-            conv_bar();
+            named_bar(2 + gi, GT);
             tc::mbar_try_wait(&rawfull[rs], rpar);              // completes at once: every thread observes the TMA phase itself
             const uint32_t rbase = raw0 + rs * g.raw_stage_bytes;
             const uint32_t a_hi = s_base + os * g.op_stage_bytes, a_lo = a_hi + g.a_op_bytes;
@@ -373,9 +390,10 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
             tc::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) { tc::mbar_arrive(&full[os]); tc::mbar_arrive(&rawempty[rs]); }
-            cons.next(g);
-            if (++rs == g.n_raw) { rs = 0; rpar ^= 1; }
-            if (++os == g.n_op) { os = 0; opar ^= 1; }
+            if (pt == 0) TL(5, tlc);
+            ++tlc;
+            n += G;
+            for (int sk = 0; sk < G && cons.valid(); ++sk) cons.next(g);
         }
     } else if (warp == MMA_WARP) {
         // ======================================= MMA ISSUER ======================================
@@ -405,8 +423,10 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
             // ulp of bias; keeping the small terms out of it cuts the number of such truncations from 3K/8 to K/8.
             const uint32_t d_corr = d_tmem + (g.acc_cols > g.BN ? g.BN : 0);
             for (int kb = w.kb0; kb < w.kb1; ++kb) {
+                if (lane == 0) TL(6, tlm);
                 mbar_wait_guard(&full[os], fpar, g.wait_mode);
                 tc::tc_fence_after();
+                if (lane == 0) TL(7, tlm);
                 if (tc::elect_one()) {
                     const uint32_t a_hi = s_base + os * g.op_stage_bytes, a_lo = a_hi + g.a_op_bytes;
                     const uint32_t b_hi = g.b_res ? s_base + g.off_bres + kb * (E::NM * g.b_op_bytes) : a_hi + b_in_stage;
@@ -431,7 +451,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
                     }
                     tc::umma_commit(&empty[os]);
                     if (kb == w.kb1 - 1) tc::umma_commit(&tfull[acc]);
-                    TL(6, tlm);
+                    TL(8, tlm);
                 }
                 ++tlm;
                 __syncwarp();
@@ -477,6 +497,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
             epi_bar();
         };
         int acc = -1;
+        int tle = 0;
         uint32_t tpar = 1;
         for (int it = blockIdx.x; it < total; it += gridDim.x, ++ni) {
             if (++acc == g.nacc) acc = 0;
@@ -485,11 +506,12 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
             const Item w = get_item(g, it);
             if (do_stats && cur_q0 >= 0 && cur_q0 != w.q0) flush(cur_q0);
             cur_q0 = w.q0;
-            {   // one polling warp per epilogue set, the others wait on a named barrier (ids 3 / 4)
+            {   // one polling warp per epilogue set, the others wait on a named barrier (ids 6 / 7; 2..5 belong to the converter groups)
                 const int set = g.split_epi ? half : 0;
                 if ((warp & 3) == 0 && (g.split_epi || warp == 0)) mbar_wait_sleep(&tfull[acc], tpar, g.epi_sleep);
-                named_bar(3 + set, g.split_epi ? 128 : EPI_T);
+                named_bar(6 + set, g.split_epi ? 128 : EPI_T);
             }
+            if (tid == 0) TL(9, 2 * ni);
             tc::tc_fence_after();
             const uint32_t t_row = tmem_base + acc * g.acc_cols + ((uint32_t)(lq * 32) << 16);
             const bool split_acc = g.acc_cols > g.BN;
@@ -502,6 +524,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
                 const int c0 = ci * 32;
                 const int ncol = min(32, g.BN - c0);
                 uint32_t r[32];
+                if (tid == 0) { TL(10, tle); ++tle; }
                 if (ncol == 32) {
                     tc::tmem_ld32(t_row + c0, r);
                 } else {
@@ -511,6 +534,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
                     for (int i = 0; i < 16; ++i) { r[i] = r16[i]; r[16 + i] = 0u; }
                 }
                 tc::tmem_ld_wait();
+                if (tid == 0) { TL(10, tle); ++tle; }
                 if (split_acc) {                // add the correction accumulator (fp32 round-to-nearest), 16 columns at a time
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
@@ -523,6 +547,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
                         }
                     }
                 }
+                if (tid == 0) { TL(10, tle); ++tle; }
                 if (ci == last_chunk) {         // accumulator drained by this warp: hand TMEM back to the MMA warp
                     tc::tc_fence_before();
                     __syncwarp();
@@ -533,6 +558,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
                     sts4(stg_u + (lane * STG_LD + 4 * j) * 4,
                          make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
                 __syncwarp();
+                if (tid == 0) { TL(10, tle); ++tle; }
                 // ---- coalesced phase: lane = (row sub-index rs, column quad cq) ----
                 const int col = w.q0 + c0 + 4 * cq;
                 const bool cok = 4 * cq < ncol && col < g.Q;
@@ -602,6 +628,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
                         }
                     }
                 }
+                if (tid == 0) { TL(10, tle); ++tle; }
                 if (do_stats) {
 #pragma unroll
                     for (int o = 8; o < 32; o <<= 1) {
@@ -619,6 +646,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
                 }
                 __syncwarp();      // staging tile is reused by the next column chunk
             }
+            if (tid == 0) TL(9, 2 * ni + 1);
         }
         if (do_stats) {
             flush(cur_q0 >= 0 ? cur_q0 : 0);       // every epilogue warp takes part (bar.sync), even one that drained no tile
@@ -705,15 +733,22 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st) {
         a.op_stage_bytes = E::NM * (a.a_op_bytes + (a.b_res ? 0 : a.b_op_bytes));
         a.raw_stage_bytes = (APT + (AMODE == XM_DY ? APT : 0) + (a.b_res ? 0 : nb_slots)) * 8192;
         if (a.b_res && a.raw_stage_bytes < (uint32_t)nb_slots * 8192) a.raw_stage_bytes = nb_slots * 8192;
-        const uint32_t fixed = EPI_W * 32 * STG_LD * 4 + EPI_W * 2 * BN * 4 + 256 + (a.b_res ? bres_bytes : 0);
-        a.n_op = 2;
-        a.n_raw = 0;
-        for (int nr = MAX_RAW; nr >= 2; --nr) {
-            if (a.n_op * a.op_stage_bytes + nr * a.raw_stage_bytes + fixed + 1088 <= SMEM_LIMIT) { a.n_raw = nr; break; }
-        }
-        if (a.n_raw == 0) continue;
+        const uint32_t fixed = EPI_W * 32 * STG_LD * 4 + EPI_W * 2 * BN * 4 + 512 + (a.b_res ? bres_bytes : 0);
+        auto fit = [&](int nop, int nraw) { return nop * a.op_stage_bytes + nraw * a.raw_stage_bytes + fixed + 1088 <= SMEM_LIMIT; };
+        if (!fit(2, 2)) continue;
         fits = true;
-        while (a.n_op < MAX_OP && (a.n_op + 1) * a.op_stage_bytes + a.n_raw * a.raw_stage_bytes + fixed + 1088 <= SMEM_LIMIT) ++a.n_op;
+        // converter groups: as many as the rings allow (every ring depth is a multiple of the group count), then deeper rings:
+        // raw stages first (they hide the TMA latency and are the cheaper ones), operand stages after
+        static int gmax = -1;
+        if (gmax < 0) { const char* e = getenv("B200SP_TCG2_GROUPS"); gmax = e ? atoi(e) : 4; if (gmax != 1 && gmax != 2 && gmax != 4) gmax = 4; }
+        int G = gmax;
+        while (G > 1 && !fit(G, G)) G >>= 1;
+        if (G == 1) { a.n_op = 2; a.n_raw = 2; } else { a.n_op = G; a.n_raw = G; }
+        a.groups = G;
+        const int step = G;
+        while (a.n_raw + step <= MAX_RAW && a.n_raw < 2 * a.n_op && fit(a.n_op, a.n_raw + step)) a.n_raw += step;
+        while (a.n_op + step <= MAX_OP && fit(a.n_op + step, a.n_raw)) a.n_op += step;
+        while (a.n_raw + step <= MAX_RAW && fit(a.n_op, a.n_raw + step)) a.n_raw += step;
         a.off_bres = a.n_op * a.op_stage_bytes;
         a.off_raw = a.off_bres + (a.b_res ? bres_bytes : 0);
         a.off_stg = a.off_raw + a.n_raw * a.raw_stage_bytes;
@@ -733,7 +768,7 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st) {
     }
     a.kb_per_split = ceil_div(a.nkb, a.splits);
     a.splits = ceil_div(a.nkb, a.kb_per_split);
-    const uint32_t smem = a.off_bar + 256 + 1024;
+    const uint32_t smem = a.off_bar + 512 + 1024;
     a.acc_cols = (2 * 2 * BN <= 512) ? 2 * BN : BN;
     a.nacc = 4 * a.acc_cols <= 512 ? 4 : 2;
     a.split_epi = (BN <= 32 && numQt == 1 && EPI_SETS == 2) ? 1 : 0;
@@ -762,6 +797,12 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st) {
 }
 
 }  // namespace
+
+#ifdef TCG_TIMELINE
+extern "C" int b200sp_tcg2_timeline(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_tcg2_tl, sizeof(long long) * 11 * 512);
+}
+#endif
 
 int tcgemm2_launch(const TcgProblem& p, cudaStream_t st) {
     if (p.dtype != B200SP_F32) return B200SP_ENOSYS;

@@ -86,7 +86,7 @@ def setup_cli(cfg):
             init_process_group('gloo')
     else:
         device = torch.device('cuda:0') if use_cuda else torch.device('cpu')
-    cfg.device = device if device.type == 'cuda' else None
+    cfg.device = str(device) if device.type == 'cuda' else None      # a string: cfg.__dict__ is dumped to config.txt as JSON
     cfg.rank, cfg.world_size = r, world
     return device
 

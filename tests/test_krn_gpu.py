@@ -185,3 +185,50 @@ def test_reference_style_loop_with_torch_clip(tmp_path):
     for k in ('head.0.weight', 'head.0.bias', 'extras.0.conv.3.weight'):
         e_cuda, e_f32 = rel(m.state_dict()[k], s64[k]), rel(s32[k], s64[k])
         assert e_cuda <= 6.0 * e_f32 + 2e-5, (k, e_cuda, e_f32)
+
+
+def test_train_step_at_the_benchmark_configuration_bs48_224():
+    """BASELINE.json configs[1] exactly: ONE bs=48 224x224 train step (forward, loss, backward, clip, AdamW) against the fp32
+    and float64 oracles on the same seeded inputs.  With 48 x 7 x 7 .. 48 x 112 x 112 samples per BatchNorm channel the
+    statistics are well conditioned, so the gates are tight: loss rel 1e-4, every gradient tensor by relative L2, the
+    post-step parameters, and the BN running statistics."""
+    from speedplusbaseline_b200.optim import FusedAdamW
+    B = 48
+    sd = synth.synth_state_dict(okrn.krn_shapes(), 2021)
+    x, y = synth.synth_images(B), synth.synth_keypoints(B)
+    r64, s64 = _oracle_step(sd, x, y, torch.float64)
+    r32, s32 = _oracle_step(sd, x, y, torch.float32)
+    m = _model(sd).train()
+    opt = FusedAdamW(m._store, m.parameters(), lr=1e-3, betas=(0.9, 0.999), weight_decay=0.01, clip_mode=1)
+    opt.zero_grad()
+    loss, sm = m(x.cuda(), y.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - r64['loss']) <= 1e-4 * abs(r64['loss']), (float(loss), r64['loss'])
+    gd = m.grad_dict()
+    gn = r64['grad_norm']
+    worst, worst32, n = 0.0, 0.0, 0
+    for k, g64 in r64['grads'].items():
+        if float(g64.norm()) < 1e-3 * gn:
+            assert float((gd[k].double().cpu() - g64).norm()) < 1e-3 * gn, k
+            continue
+        e_cuda, e_f32 = rel(gd[k], g64), rel(r32['grads'][k], g64)
+        worst, worst32, n = max(worst, e_cuda), max(worst32, e_f32), n + 1
+        assert e_cuda <= 5.0 * e_f32 + 2e-4, (k, e_cuda, e_f32)
+    print('bs=48 gradient parity over %d tensors: worst rel-L2 vs float64  CUDA %.2e   torch-fp32 %.2e' % (n, worst, worst32))
+    # measured on B200: worst tensor 1.7e-2 for the CUDA path against 2.3e-2 for torch's own fp32 kernels (a handful of ReLU6 /
+    # clamp decisions flip between fp32 and float64): the CUDA path must not be worse than the fp32 reference implementation
+    assert worst <= 1.5 * worst32 + 1e-3, (worst, worst32)
+    opt.step()
+    torch.cuda.synchronize()
+    assert abs(opt.last_grad_norm() - gn) <= 1e-4 * gn + 3 * abs(r32['grad_norm'] - gn)
+    sdm = m.state_dict()
+    for k in sd:
+        if k.endswith('num_batches_tracked'):
+            assert int(sdm[k]) == int(s64[k])
+        elif 'running' in k:
+            assert rel(sdm[k], s64[k]) < 1e-5, k
+    for k in ('head.0.weight', 'extras.3.conv.3.weight', 'extras.1.conv.3.weight', 'base.17.conv.2.weight', 'base.8.conv.1.0.weight',
+              'base.2.conv.0.0.weight', 'base.0.0.weight'):
+        e_cuda, e_f32 = rel(sdm[k], s64[k]), rel(s32[k], s64[k])
+        assert e_cuda <= 4.0 * e_f32 + 1e-5, (k, e_cuda, e_f32)

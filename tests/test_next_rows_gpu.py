@@ -83,8 +83,14 @@ def test_fused_optimizer_classes_match_oracle(name, clip_mode):
             ooptim.adam_step(ref_p, gl, ost, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, wd=0.01)
         torch.cuda.synchronize()
         assert rel(st.params, ref_p[0]) < 2e-6, it
-    sd = opt.state_dict()
-    assert sd['state']['step'] == 4 and (sd['state']['exp_avg_sq'] is None) == (name != 'adam')
+    sd = opt.state_dict()                      # torch's own checkpoint layout: per-parameter state in the reference shapes
+    n1 = {'sgd': 'momentum_buffer', 'rmsprop': 'square_avg', 'adam': 'exp_avg'}[name]
+    assert len(sd['state']) == 4 and sd['param_groups'][0]['params'] == [0, 1, 2, 3]       # a.weight, b.weight, bn.weight, bn.bias
+    assert tuple(sd['state'][0][n1].shape) == (37, 5) and tuple(sd['state'][3][n1].shape) == (8,)
+    assert ('exp_avg_sq' in sd['state'][0]) == (name == 'adam')
+    if name != 'sgd':
+        assert float(sd['state'][1]['step']) == 4.0
+    assert opt.device_step() == 4
     assert rel(opt.exp_avg, ost.s1[0]) < 1e-5
 
 
