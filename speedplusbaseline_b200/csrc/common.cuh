@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <utility>
 #include "b200sp.h"
 
 extern long long g_b200sp_launches;      // defined in misc.cu
@@ -10,6 +12,24 @@ extern long long g_b200sp_launches;      // defined in misc.cu
 #define B200SP_RETURN_LAST()  do { cudaError_t e__ = cudaGetLastError(); return (int)e__; } while (0)
 
 #define NUM_SMS 148
+
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------
+// A kernel launched with b200sp_launch_pdl() may start (block scheduling, barrier / TMEM / tensor-map set-up) while its
+// predecessor in the stream is still draining; it must execute pdl_wait() before it touches any global memory, and it calls
+// pdl_trigger() early so that ITS successor can do the same.  Both are no-ops for a normally launched kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool b200sp_pdl_enabled();               // misc.cu: env B200SP_PDL (default on)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t b200sp_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = b200sp_pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 typedef __nv_bfloat16 bf16;
 

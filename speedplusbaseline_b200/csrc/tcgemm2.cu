@@ -294,6 +294,9 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
+    // everything above touched only shared memory / TMEM: under programmatic dependent launch it overlapped the predecessor's tail
+    pdl_trigger();
+    pdl_wait();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);      // broadcast form: keeps the TMEM address (and everything derived from it) in UNIFORM registers, so tcgen05.mma needs no per-instruction R2UR waterfall
     const uint32_t b_in_stage = E::NM * g.a_op_bytes;
     constexpr int slotA2 = APT, slotB = AMODE == XM_DY ? 2 * APT : APT;     // 8192-byte sub-slots of a raw stage: A | [A2] | B
@@ -506,6 +509,25 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
             const Item w = get_item(g, it);
             if (do_stats && cur_q0 >= 0 && cur_q0 != w.q0) flush(cur_q0);
             cur_q0 = w.q0;
+            if (EPI == TCG_EPI_DGRAD && (g.has_bnb || g.skip)) {
+                // the saved conv output y (activation mask / BN reductions) and the skip gradient of this tile are pulled into L2
+                // now, while the main loop still runs: the epilogue's loads then cost an L2 hit instead of a DRAM round trip
+                // (r2g timeline: 7-9 k cycles per column chunk were spent waiting on them)
+                for (int ci = c_first; ci < nchunks; ci += c_step) {
+                    const int col = w.q0 + ci * 32 + 4 * cq;
+                    if (col < g.Q) {
+#pragma unroll
+                        for (int ps = 0; ps < 8; ++ps) {
+                            const int row = w.p0 + lq * 32 + rs + ps * 4;
+                            if (row < g.P) {
+                                const size_t off = (size_t)row * g.ldo + col;
+                                if (g.has_bnb) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const T*>(g.bnb.y) + off));
+                                if (g.skip) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const T*>(g.skip) + off));
+                            }
+                        }
+                    }
+                }
+            }
             {   // one polling warp per epilogue set, the others wait on a named barrier (ids 6 / 7; 2..5 belong to the converter groups)
                 const int set = g.split_epi ? half : 0;
                 if ((warp & 3) == 0 && (g.split_epi || warp == 0)) mbar_wait_sleep(&tfull[acc], tpar, g.epi_sleep);
@@ -525,6 +547,8 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
                 const int ncol = min(32, g.BN - c0);
                 uint32_t r[32];
                 if (tid == 0) { TL(10, tle); ++tle; }
+                // the main accumulator and the first half of the correction accumulator are requested together (one wait for both)
+                uint32_t q16[16];
                 if (ncol == 32) {
                     tc::tmem_ld32(t_row + c0, r);
                 } else {
@@ -533,18 +557,19 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
 #pragma unroll
                     for (int i = 0; i < 16; ++i) { r[i] = r16[i]; r[16 + i] = 0u; }
                 }
+                constexpr bool MERGE_LD = EPI != TCG_EPI_DGRAD;      // the dgrad epilogue is register-bound: it keeps the loads apart
+                if (MERGE_LD && split_acc) tc::tmem_ld16(t_row + g.BN + c0, q16);
                 tc::tmem_ld_wait();
                 if (tid == 0) { TL(10, tle); ++tle; }
                 if (split_acc) {                // add the correction accumulator (fp32 round-to-nearest), 16 columns at a time
+                    if (!MERGE_LD) { tc::tmem_ld16(t_row + g.BN + c0, q16); tc::tmem_ld_wait(); }
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        if (hh * 16 < ncol) {
-                            uint32_t q16[16];
-                            tc::tmem_ld16(t_row + g.BN + c0 + hh * 16, q16);
-                            tc::tmem_ld_wait();
+                    for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(q16[i]));
+                    if (16 < ncol) {
+                        tc::tmem_ld16(t_row + g.BN + c0 + 16, q16);
+                        tc::tmem_ld_wait();
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) r[hh * 16 + i] = __float_as_uint(__uint_as_float(r[hh * 16 + i]) + __uint_as_float(q16[i]));
-                        }
+                        for (int i = 0; i < 16; ++i) r[16 + i] = __float_as_uint(__uint_as_float(r[16 + i]) + __uint_as_float(q16[i]));
                     }
                 }
                 if (tid == 0) { TL(10, tle); ++tle; }
@@ -740,8 +765,10 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st) {
         // converter groups: as many as the rings allow (every ring depth is a multiple of the group count), then deeper rings:
         // raw stages first (they hide the TMA latency and are the cheaper ones), operand stages after
         static int gmax = -1;
-        if (gmax < 0) { const char* e = getenv("B200SP_TCG2_GROUPS"); gmax = e ? atoi(e) : 4; if (gmax != 1 && gmax != 2 && gmax != 4) gmax = 4; }
-        int G = gmax;
+        // measured (profiles/r2_gemm_groups.txt): 2 groups are worth ~4 % on the long-M data-gradient shapes, 4 bring nothing
+        // more (the MMA issue thread becomes the critical path), and the MN-major weight-gradient form is fastest with one
+        if (gmax < 0) { const char* e = getenv("B200SP_TCG2_GROUPS"); gmax = e ? atoi(e) : 2; if (gmax != 1 && gmax != 2 && gmax != 4) gmax = 2; }
+        int G = EPI == TCG_EPI_ATOMIC ? 1 : gmax;
         while (G > 1 && !fit(G, G)) G >>= 1;
         if (G == 1) { a.n_op = 2; a.n_raw = 2; } else { a.n_op = G; a.n_raw = G; }
         a.groups = G;
@@ -791,7 +818,7 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st) {
     if (rc) return rc;
     const int total = numPt * numQt * a.splits;
     const int grid = total < NUM_SMS ? total : NUM_SMS;
-    kern<<<grid, NT, smem, st>>>(a);
+    { cudaError_t le = b200sp_launch_pdl(kern, dim3(grid), dim3(NT), smem, st, a); if (le != cudaSuccess) return (int)le; }
     B200SP_COUNT_LAUNCH();
     B200SP_RETURN_LAST();
 }
