@@ -185,6 +185,17 @@ def secondary_workloads(dev, stepper, d_img, d_tgt, k=8):
     from speedplusbaseline_b200.core.dann import DANNTrainStep
     from speedplusbaseline_b200.core.trainer import SPNTrainStep
     out = {}
+    # BASELINE.json configs[1] "(fp32 and --use_fp16)": the same step with the --use_fp16 mode of this path
+    from speedplusbaseline_b200.nets.park2019 import KeypointRegressionNet
+    mt = KeypointRegressionNet(11, device=dev, seed=2021, tf32_gemm=True)
+    mt.train()
+    ot = FusedAdamW(mt._store, mt.parameters(), lr=1e-3, weight_decay=0.01, clip_mode=1)
+    from speedplusbaseline_b200.core.trainer import KRNTrainStep
+    stt = KRNTrainStep(mt, ot)
+    ms = _time_steps(lambda: stt.step(d_img, d_tgt), 5, 30)
+    out['krn_train_use_fp16_bs48'] = {'ms': ms, 'images_per_sec': BATCH / ms * 1e3, 'dtype': 'tf32',
+                                      'math': 'fp32 storage, single-pass TF32 GEMMs (the --use_fp16 mode)'}
+    del mt, ot, stt
     from speedplusbaseline_b200.styleaug.ghiasi import synthetic_state
     from speedplusbaseline_b200.styleaug.styleAugmentor import checkpoint_dir
     try:                                                         # the reference's REAL checkpoints (staged with baseline/_ref)
@@ -255,7 +266,8 @@ def main():
     ap.add_argument('--no-secondary', action='store_true')
     ap.add_argument('--no-reference-cuda', action='store_true', help='skip the reference-on-cuDNN secondaries')
     ap.add_argument('--workload', default='krn', choices=['krn', 'dann'], help='dann = BASELINE.json configs[3] (adapt.py step, 48 source + 48 target images per GPU)')
-    ap.add_argument('--dtype', default='fp32', choices=['fp32', 'bf16'], help='bf16 = the --use_fp16 path (secondary number; the headline is fp32)')
+    ap.add_argument('--dtype', default='fp32', choices=['fp32', 'tf32', 'bf16'],
+                    help='tf32 = the --use_fp16 mode (fp32 storage, single-pass TF32 GEMMs); bf16 = experimental bf16-storage engine; the headline is fp32')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -290,7 +302,7 @@ def main():
         h_tim = torch.rand(BATCH, 3, HW, HW, generator=g).pin_memory()          # unlabeled target-domain batch
         host_batch = (h_img, h_tgt, h_tim)
     else:
-        model = KeypointRegressionNet(11, device=dev, seed=2021, dtype=L.BF16 if args.dtype == 'bf16' else L.F32)
+        model = KeypointRegressionNet(11, device=dev, seed=2021, dtype=L.BF16 if args.dtype == 'bf16' else L.F32, tf32_gemm=args.dtype == 'tf32')
         host_batch = (h_img, h_tgt)
     model.train()
     opt = FusedAdamW(model._store, model.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
@@ -367,8 +379,9 @@ def main():
             math = 'fp32 storage, 3xTF32 tensor-core GEMMs + fp32 CUDA-core stencils (DANN is fp32-only in the reference, adapt.py:99-101)'
         else:
             metric, workload = METRIC, 'KRN train bs=48/GPU AdamW 224x224 synthetic (BASELINE.json configs[1])'
-            math = ('fp32 storage, 3xTF32 tensor-core GEMMs + fp32 CUDA-core stencils' if args.dtype == 'fp32' else
-                    'bf16 storage + bf16 tensor-core GEMMs, fp32 accumulate / statistics / master weights')
+            math = {'fp32': 'fp32 storage, 3xTF32 tensor-core GEMMs + fp32 CUDA-core stencils',
+                    'tf32': '--use_fp16 mode: fp32 storage, single-pass TF32 tensor-core GEMMs (fp16 operand mantissa, fp32 range / accumulate), fp32 everything else',
+                    'bf16': 'bf16 storage + bf16 tensor-core GEMMs, fp32 accumulate / statistics / master weights (experimental)'}[args.dtype]
         line = {
             'metric': metric, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,

@@ -31,6 +31,10 @@ extern "C" {
 
 #define B200SP_F32 0
 #define B200SP_BF16 1
+/* accepted by the b200sp_pw_* GEMM entry points only: fp32 storage, SINGLE-pass TF32 tensor-core math (operands rounded to a
+ * 10-bit mantissa -- fp16's -- with fp32 range and fp32 accumulation).  This is what `--use_fp16` selects (config.py:39,
+ * trainer.py:73-94): the autocast numerics of the GEMMs without a loss scaler, because the exponent range stays fp32's. */
+#define B200SP_F32_TF32X1 2
 
 #define B200SP_ACT_NONE 0
 #define B200SP_ACT_RELU 1

@@ -7,7 +7,7 @@ import torch
 
 from . import _build
 
-F32, BF16 = 0, 1
+F32, BF16, F32_TF32X1 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_RELU6, ACT_LEAKY02, ACT_SIGMOID = 0, 1, 2, 3, 4
 VT_PLAIN, VT_BNACT, VT_DY = 0, 1, 2
 OPT_ADAMW, OPT_SGD, OPT_RMSPROP, OPT_ADAM = 0, 1, 2, 3

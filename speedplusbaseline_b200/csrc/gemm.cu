@@ -331,10 +331,11 @@ inline bool prefer_cuda_cores(int op, int M, int N, int K) {
     if (op == 1) { for (auto& e : dgrad_nk) if (e[0] == N && e[1] == K) return true; }
     return false;
 }
-// second-generation tcgen05 kernel (tcgemm2.cu: TMA raw ring + lean converters); B200SP_TCG2=0 keeps the first-generation dispatch
+// second-generation tcgen05 kernel (tcgemm2.cu: TMA raw ring + lean converters) takes every shape it supports;
+// B200SP_TCG2=0 restores the first-generation dispatch (tcgemm.cu + the measured mma.sync table) for A/B runs
 inline bool tcg2_on() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("B200SP_TCG2"); v = (e && e[0] == '1') ? 1 : 0; }
+    if (v < 0) { const char* e = getenv("B200SP_TCG2"); v = (e && e[0] == '0') ? 0 : 1; }      // default on (validated on B200, round 2)
     return v != 0;
 }
 inline bool tcg2_wgrad_on() {      // the weight-gradient form (both operands MN-major) can be switched separately: B200SP_TCG2_WGRAD=0
@@ -352,6 +353,15 @@ inline bool use_tc(int op, int M, int N, int K) {
 extern "C" int b200sp_pw_fwd(const b200sp_vtensor* x, const float* w, const float* bias, int out_act, void* y,
                              const b200sp_bnfwd* bn, int M, int N, int K, int dtype, void* stream) {
     if (!x || x->mode == B200SP_VT_DY) return B200SP_EINVAL;
+    if (dtype == B200SP_F32_TF32X1) {    // --use_fp16 mode: second-generation kernel only
+        TcgProblem p = {};
+        p.a = *x; p.b = plain_vt(w); p.a_lay = TCG_LAY_KM; p.b_lay = TCG_LAY_KM;
+        p.P = M; p.Q = N; p.R = K; p.lda = K; p.ldb = K; p.epi = TCG_EPI_FWD; p.dtype = dtype;
+        p.out = y; p.bias = bias; p.out_act = out_act; p.bnf = bn; p.count = (double)M;
+        const int rc = tcgemm2_launch(p, (cudaStream_t)stream);
+        if (rc != B200SP_ENOSYS) return rc;
+        dtype = B200SP_F32;              // shapes the kernel does not take run at full precision
+    }
     if (dtype == B200SP_F32) {           // round-2 candidate (B200SP_PWDIRECT=1): exact-fp32 FFMA kernel for the long-M / tiny-N*K shapes
         const int rc = pwdirect_fwd(x, w, bias, out_act, (float*)y, bn, M, N, K, (cudaStream_t)stream);
         if (rc != B200SP_ENOSYS) return rc;
@@ -380,6 +390,15 @@ extern "C" int b200sp_pw_fwd(const b200sp_vtensor* x, const float* w, const floa
 extern "C" int b200sp_pw_dgrad(const b200sp_vtensor* dy, const float* w, const void* skip, float scale_out, void* g,
                                const b200sp_bnbwd* bn, int M, int N, int K, int dtype, void* stream) {
     if (!dy) return B200SP_EINVAL;
+    if (dtype == B200SP_F32_TF32X1) {
+        TcgProblem p = {};
+        p.a = *dy; p.b = plain_vt(w); p.a_lay = TCG_LAY_KM; p.b_lay = TCG_LAY_MM;
+        p.P = M; p.Q = K; p.R = N; p.lda = N; p.ldb = K; p.epi = TCG_EPI_DGRAD; p.dtype = dtype;
+        p.out = g; p.skip = skip; p.scale_out = scale_out; p.bnb = bn; p.count = (double)M;
+        const int rc = tcgemm2_launch(p, (cudaStream_t)stream);
+        if (rc != B200SP_ENOSYS) return rc;
+        dtype = B200SP_F32;
+    }
     if (dtype == B200SP_F32) {           // round-2 candidate (B200SP_PWDIRECT=1)
         const int rc = pwdirect_dgrad(dy, w, (const float*)skip, scale_out, (float*)g, bn, M, N, K, (cudaStream_t)stream);
         if (rc != B200SP_ENOSYS) return rc;
@@ -412,6 +431,16 @@ extern "C" int b200sp_pw_dgrad(const b200sp_vtensor* dy, const float* w, const v
 extern "C" int b200sp_pw_wgrad(const b200sp_vtensor* dy, const b200sp_vtensor* x, float* dw, float* dbias,
                                int M, int N, int K, int dtype, void* stream) {
     if (!dy || !x || x->mode == B200SP_VT_DY) return B200SP_EINVAL;
+    if (dtype == B200SP_F32_TF32X1) {
+        TcgProblem p = {};
+        p.a = *dy; p.b = *x; p.a_lay = TCG_LAY_MM; p.b_lay = TCG_LAY_MM;
+        p.P = N; p.Q = K; p.R = M; p.lda = N; p.ldb = K; p.epi = TCG_EPI_ATOMIC; p.dtype = dtype;
+        p.out = dw;
+        const int rc = tcgemm2_launch(p, (cudaStream_t)stream);
+        if (rc == 0 && dbias) return b200sp_colsum_f32(dy, dbias, M, N, B200SP_F32, stream);
+        if (rc != B200SP_ENOSYS) return rc;
+        dtype = B200SP_F32;
+    }
     if (dtype == B200SP_BF16 || tcg2_on() || use_tc(2, M, N, K)) {
         TcgProblem p = {};
         p.a = *dy; p.b = *x; p.a_lay = TCG_LAY_MM; p.b_lay = TCG_LAY_MM;

@@ -54,6 +54,7 @@ struct alignas(64) Tcg2Args {
     int P, Q, R, lda, ldb, ldo;
     int BN, numPt, numQt, splits, kb_per_split, nkb;
     int n_op, n_raw, groups;
+    int nm;                          // operand copies per tile: 2 = (tf32 hi, lo) for 3xTF32, 1 = single-pass TF32 (--use_fp16 mode)
     int b_res;
     int ac_last, nks_last;
     int b_atoms;                     // MN-major B: 128-byte atoms per tile
@@ -164,7 +165,13 @@ __device__ __forceinline__ void split1(float v, float& hi, float& lo) {
     hi = __uint_as_float(h);
     lo = __uint_as_float((__float_as_uint(v - hi) + 0x1000u) & 0xffffe000u);
 }
-__device__ __forceinline__ void split_store(float4 v, uint32_t dst_hi, uint32_t dst_lo) {
+__device__ __forceinline__ float tf32_rn(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
+// single == true: only the rounded tf32 value is stored (one MMA per k-step instead of three)
+__device__ __forceinline__ void split_store(float4 v, uint32_t dst_hi, uint32_t dst_lo, bool single) {
+    if (single) {
+        sts4(dst_hi, make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w)));
+        return;
+    }
     float4 h, l;
     split1(v.x, h.x, l.x); split1(v.y, h.y, l.y); split1(v.z, h.z, l.z); split1(v.w, h.w, l.w);
     sts4(dst_hi, h);
@@ -184,12 +191,14 @@ struct Conv {
     ActP act;
     int R, nkb, ac_last, mn_ext;
     int gc, pg, GT, npieces;
+    bool single;
     uint32_t soff;
     XfP par;
     __device__ __forceinline__ void init(const b200sp_vtensor& t, int mn_ext_, int R_, int nkb_, int ac_last_, int pg_, int GT_, int tile_rows) {
         vt = t; act = act_params(t.act);
         R = R_; nkb = nkb_; ac_last = ac_last_; mn_ext = mn_ext_;
         pg = pg_; GT = GT_;
+        single = false;
         gc = pg & 7;
         if (LAY == TCG_LAY_KM) {
             soff = tc::sw128_off(pg >> 3, gc);
@@ -206,37 +215,38 @@ struct Conv {
             xf_load<MODE>(vt, ch, par);
         }
     }
+    __device__ __forceinline__ void piece(int kb, int mn0, int q, uint32_t o, uint32_t raw, uint32_t raw2, uint32_t op_hi, uint32_t op_lo) {
+        const float4 r = lds4(raw + o);
+        float4 r2 = f4zero();
+        if (MODE == XM_DY) r2 = lds4(raw2 + o);
+        float4 v;
+        if (LAY == TCG_LAY_KM) {
+            v = xf_apply<MODE>(r, r2, par, act);
+        } else {
+            v = r;
+            if (MODE != XM_PLAIN) {
+                int ch = mn0 + (q >> 8) * 32 + gc * 4;
+                ch = min(ch, mn_ext - 4);
+                xf_load<MODE>(vt, ch, par);
+                v = xf_apply<MODE>(r, r2, par, act);
+                // reduction rows beyond R were zero-filled by the TMA unit, but a transformed zero is not zero: mask them
+                if (kb * 32 + ((q >> 3) & 31) >= R) v = f4zero();
+            }
+        }
+        split_store(v, op_hi + soff + o, op_lo + soff + o, single);
+    }
     // raw / raw2: this thread's piece 0 in the raw stage (stage base + operand offset + pg*16); op_hi / op_lo: operand tile bases
     __device__ __forceinline__ void convert(int kb, int mn0, uint32_t raw, uint32_t raw2, uint32_t op_hi, uint32_t op_lo) {
-        const uint32_t step = (uint32_t)GT * 16u;
-        if (LAY == TCG_LAY_KM) {
-            if (kb == nkb - 1 && gc >= ac_last) return;           // partial last k-block: the MMA never reads these chunks
-            uint32_t o = 0;
-#pragma unroll 2
-            for (int q = pg; q < npieces; q += GT, o += step) {
-                const float4 r = lds4(raw + o);
-                float4 r2 = f4zero();
-                if (MODE == XM_DY) r2 = lds4(raw2 + o);
-                split_store(xf_apply<MODE>(r, r2, par, act), op_hi + soff + o, op_lo + soff + o);
-            }
+        if (LAY == TCG_LAY_KM && kb == nkb - 1 && gc >= ac_last) return;      // partial last k-block: the MMA never reads these chunks
+        if (GT == PROD_T) {                 // one group: at most APT pieces per thread, fully unrolled (independent lds / sts chains)
+#pragma unroll
+            for (int i = 0; i < APT; ++i)
+                if (pg + i * PROD_T < npieces) piece(kb, mn0, pg + i * PROD_T, (uint32_t)i * (PROD_T * 16), raw, raw2, op_hi, op_lo);
         } else {
+            const uint32_t step = (uint32_t)GT * 16u;
             uint32_t o = 0;
 #pragma unroll 2
-            for (int q = pg; q < npieces; q += GT, o += step) {
-                const float4 r = lds4(raw + o);
-                float4 r2 = f4zero();
-                if (MODE == XM_DY) r2 = lds4(raw2 + o);
-                float4 v = r;
-                if (MODE != XM_PLAIN) {
-                    int ch = mn0 + (q >> 8) * 32 + gc * 4;
-                    ch = min(ch, mn_ext - 4);
-                    xf_load<MODE>(vt, ch, par);
-                    v = xf_apply<MODE>(r, r2, par, act);
-                    // reduction rows beyond R were zero-filled by the TMA unit, but a transformed zero is not zero: mask them
-                    if (kb * 32 + ((q >> 3) & 31) >= R) v = f4zero();
-                }
-                split_store(v, op_hi + soff + o, op_lo + soff + o);
-            }
+            for (int q = pg; q < npieces; q += GT, o += step) piece(kb, mn0, q, o, raw, raw2, op_hi, op_lo);
         }
     }
 };
@@ -298,7 +308,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
     pdl_trigger();
     pdl_wait();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);      // broadcast form: keeps the TMEM address (and everything derived from it) in UNIFORM registers, so tcgen05.mma needs no per-instruction R2UR waterfall
-    const uint32_t b_in_stage = E::NM * g.a_op_bytes;
+    const uint32_t b_in_stage = g.nm * g.a_op_bytes;
     constexpr int slotA2 = APT, slotB = AMODE == XM_DY ? 2 * APT : APT;     // 8192-byte sub-slots of a raw stage: A | [A2] | B
 
     if (warp == TMA_WARP) {
@@ -347,6 +357,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
         Conv<BLAY, BMODE> CB;
         CA.init(g.a, g.P, g.R, g.nkb, g.ac_last, pg, GT, BM);
         CB.init(g.b, g.Q, g.R, g.nkb, g.ac_last, pg, GT, g.BN);
+        CA.single = CB.single = g.nm == 1;
         const uint32_t raw0 = s_base + g.off_raw + pg * 16;
         int n = gi;                                              // sequence number of the k-block this group converts next
         const int nb = g.b_res ? g.nkb : 0;
@@ -356,7 +367,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
             if (poller) mbar_wait_guard(&rawfull[rs], rpar);
             named_bar(2 + gi, GT);
             tc::mbar_try_wait(&rawfull[rs], rpar);              // completes at once: every thread observes the TMA phase itself
-            const uint32_t b_hi = s_base + g.off_bres + n * (E::NM * g.b_op_bytes), b_lo = b_hi + g.b_op_bytes;
+            const uint32_t b_hi = s_base + g.off_bres + n * (g.nm * g.b_op_bytes), b_lo = b_hi + g.b_op_bytes;
             CB.load_params(n);
             CB.convert(n, 0, raw0 + rs * g.raw_stage_bytes, 0, b_hi, b_lo);
             __syncwarp();
@@ -432,7 +443,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
                 if (lane == 0) TL(7, tlm);
                 if (tc::elect_one()) {
                     const uint32_t a_hi = s_base + os * g.op_stage_bytes, a_lo = a_hi + g.a_op_bytes;
-                    const uint32_t b_hi = g.b_res ? s_base + g.off_bres + kb * (E::NM * g.b_op_bytes) : a_hi + b_in_stage;
+                    const uint32_t b_hi = g.b_res ? s_base + g.off_bres + kb * (g.nm * g.b_op_bytes) : a_hi + b_in_stage;
                     const uint32_t b_lo = b_hi + g.b_op_bytes;
                     // a K-major operand only holds the active chunks of a partial last k-block: never read beyond them
                     const int nks = ((ALAY == TCG_LAY_KM || BLAY == TCG_LAY_KM) && kb == g.nkb - 1) ? g.nks_last : 4;
@@ -442,13 +453,13 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
                     for (int ks = 0; ks < 4; ++ks) {
                         if (ks < nks) {
                             const uint32_t accum = ks > 0 ? 1u : first;
-                            if (E::TF32) {
+                            if (g.nm == 2) {
                                 const bool split = g.acc_cols > g.BN;
                                 tc::umma<true>(d_corr, mk(al + ks * A_STEP, A_HIW), mk(bh + ks * B_STEP, B_HIW), idesc, accum);
                                 tc::umma<true>(d_corr, mk(ah + ks * A_STEP, A_HIW), mk(bl + ks * B_STEP, B_HIW), idesc, 1u);
                                 tc::umma<true>(d_tmem, mk(ah + ks * A_STEP, A_HIW), mk(bh + ks * B_STEP, B_HIW), idesc, split ? accum : 1u);
-                            } else {
-                                tc::umma<false>(d_tmem, mk(ah + ks * A_STEP, A_HIW), mk(bh + ks * B_STEP, B_HIW), idesc, accum);
+                            } else {        // single-pass TF32: one MMA per k-step on the rounded operands
+                                tc::umma<true>(d_tmem, mk(ah + ks * A_STEP, A_HIW), mk(bh + ks * B_STEP, B_HIW), idesc, accum);
                             }
                         }
                     }
@@ -753,9 +764,9 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st) {
         a.b_atoms = ceil_div(BN * E::ES, 128);
         a.b_op_bytes = BLAY == TCG_LAY_KM ? BN * 128 : a.b_atoms * E::KE * 128;
         const int nb_slots = ceil_div((int)a.b_op_bytes, 8192);
-        const uint32_t bres_bytes = (uint32_t)a.nkb * E::NM * a.b_op_bytes;
+        const uint32_t bres_bytes = (uint32_t)a.nkb * a.nm * a.b_op_bytes;
         a.b_res = (EPI != TCG_EPI_ATOMIC && numQt == 1 && BMODE == XM_PLAIN && bres_bytes <= BRES_LIMIT) ? 1 : 0;
-        a.op_stage_bytes = E::NM * (a.a_op_bytes + (a.b_res ? 0 : a.b_op_bytes));
+        a.op_stage_bytes = a.nm * (a.a_op_bytes + (a.b_res ? 0 : a.b_op_bytes));
         a.raw_stage_bytes = (APT + (AMODE == XM_DY ? APT : 0) + (a.b_res ? 0 : nb_slots)) * 8192;
         if (a.b_res && a.raw_stage_bytes < (uint32_t)nb_slots * 8192) a.raw_stage_bytes = nb_slots * 8192;
         const uint32_t fixed = EPI_W * 32 * STG_LD * 4 + EPI_W * 2 * BN * 4 + 512 + (a.b_res ? bres_bytes : 0);
@@ -796,7 +807,7 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st) {
     a.kb_per_split = ceil_div(a.nkb, a.splits);
     a.splits = ceil_div(a.nkb, a.kb_per_split);
     const uint32_t smem = a.off_bar + 512 + 1024;
-    a.acc_cols = (2 * 2 * BN <= 512) ? 2 * BN : BN;
+    a.acc_cols = (a.nm == 2 && 2 * 2 * BN <= 512) ? 2 * BN : BN;
     a.nacc = 4 * a.acc_cols <= 512 ? 4 : 2;
     a.split_epi = (BN <= 32 && numQt == 1 && EPI_SETS == 2) ? 1 : 0;
     uint32_t cols = 32;
@@ -832,7 +843,7 @@ extern "C" int b200sp_tcg2_timeline(long long* host_out) {
 #endif
 
 int tcgemm2_launch(const TcgProblem& p, cudaStream_t st) {
-    if (p.dtype != B200SP_F32) return B200SP_ENOSYS;
+    if (p.dtype != B200SP_F32 && p.dtype != B200SP_F32_TF32X1) return B200SP_ENOSYS;
     if (p.Q % 4 || p.lda % 4 || p.ldb % 4) return B200SP_ENOSYS;
     if (p.a_lay == TCG_LAY_KM ? (p.R % 4) : (p.P % 4)) return B200SP_ENOSYS;
     if (p.b_lay == TCG_LAY_KM ? (p.R % 4) : (p.Q % 4)) return B200SP_ENOSYS;
@@ -853,6 +864,7 @@ int tcgemm2_launch(const TcgProblem& p, cudaStream_t st) {
     if (p.bnb) a.bnb = *p.bnb;
     a.count = p.count;
     a.epi_sleep = 512;
+    a.nm = p.dtype == B200SP_F32_TF32X1 ? 1 : 2;
     const int am = p.a.mode, bm = p.b.mode;
     if (p.epi == TCG_EPI_FWD && p.a_lay == TCG_LAY_KM && p.b_lay == TCG_LAY_KM && bm == B200SP_VT_PLAIN) {
         if (am == B200SP_VT_PLAIN) return launch_cfg<TCG_LAY_KM, TCG_LAY_KM, TCG_EPI_FWD, XM_PLAIN, XM_PLAIN>(a, st);

@@ -99,10 +99,13 @@ class _Ctx:
 
 
 class KRNEngine:
-    def __init__(self, num_keypoints=11, prefix='', dann=False, device=None, dtype=L.F32):
+    def __init__(self, num_keypoints=11, prefix='', dann=False, device=None, dtype=L.F32, tf32_gemm=False):
+        """tf32_gemm: the `--use_fp16` mode -- fp32 storage everywhere, 1x1-convolution GEMMs in SINGLE-pass TF32 (fp16's 10-bit
+        operand mantissa with fp32 range and accumulation; include/b200sp.h B200SP_F32_TF32X1)."""
         L.require_cuda()
         self.device = torch.device(device if device is not None else 'cuda:0')
         self.prefix, self.dann, self.dtype = prefix, dann, dtype
+        self.gemm_dtype = L.F32_TF32X1 if (tf32_gemm and dtype == L.F32) else dtype
         self.nk, self.N = num_keypoints, 2 * num_keypoints
         W, BN, self.key_order = krn_layout(num_keypoints, prefix, dann)
         self.store = ParamStore(W, BN, self.device)
@@ -177,6 +180,7 @@ class KRNEngine:
         """b200sp_pw_wgrad on the side stream: a layer's weight gradient and its data gradient are independent
         consumers of dY, and each of these GEMMs leaves most SMs idle (few tiles, latency-bound), so they overlap.
         Fork after the kernel that produced dY (event), join at the end of backward().  Works under graph capture."""
+        args = args[:-1] + (self.gemm_dtype,)
         if not self._async_wgrad:
             L.call('b200sp_pw_wgrad', *args, L.stream_ptr())
             return
@@ -204,7 +208,7 @@ class KRNEngine:
     def _pw_fwd(self, cx, xvt, wkey, bn_p, M, N, K, train, name, bias=None, out_act=L.ACT_NONE, shape=None):
         y = self._buf(cx.Y, name, shape)
         bn = self._bnfwd(cx, self._bi(bn_p), train) if bn_p else None
-        L.call('b200sp_pw_fwd', C.byref(xvt), self._wq(wkey), bias, out_act, y.data_ptr(), bn, M, N, K, self.dtype, L.stream_ptr())
+        L.call('b200sp_pw_fwd', C.byref(xvt), self._wq(wkey), bias, out_act, y.data_ptr(), bn, M, N, K, self.gemm_dtype, L.stream_ptr())
         return y
 
     def _dw_fwd(self, cx, xvt, wkey, bn_p, B, H, W, Cc, stride, train, name):
@@ -323,7 +327,7 @@ class KRNEngine:
                         B * h13 * w13, 64, 96, dt)
             d13p = self._buf(cx.dO, '13r', cx.O[13].shape)
             L.call('b200sp_pw_dgrad', C.byref(dyr), self._wq('extras.2.conv.0.weight'), None, 1.0, d13p.data_ptr(), None,
-                   B * h13 * w13, 64, 96, dt, sp)
+                   B * h13 * w13, 64, 96, self.gemm_dtype, sp)
             # ---- extras.1, extras.0
             vt_e0 = self._vt_bnact(cx, cx.Y['xp0'], self._bi('extras.0.conv.4'), L.ACT_RELU)
             g_e0p = self._buf(cx.G, 'xp0', cx.Y['xp0'].shape)
@@ -349,7 +353,7 @@ class KRNEngine:
             self._wgrad(C.byref(dyp), C.byref(dvt), self._wg('%s.%d.weight' % (p, j + 1)), None, Mo, cout, hid, dt)
             gd = self._buf(cx.G, 'd%d' % i, yd.shape)
             L.call('b200sp_pw_dgrad', C.byref(dyp), self._wq('%s.%d.weight' % (p, j + 1)), None, 1.0, gd.data_ptr(),
-                   self._bnbwd(cx, bid, yd, L.ACT_RELU6), Mo, cout, hid, dt, sp)
+                   self._bnbwd(cx, bid, yd, L.ACT_RELU6), Mo, cout, hid, self.gemm_dtype, sp)
             dyd = self._vt_dy(cx, gd, yd, bid)
             if t != 1:
                 ye, bie = cx.Y['e%d' % i], self._bi(p + '.0.1')
@@ -367,7 +371,7 @@ class KRNEngine:
                 tprev = self.blocks[i - 2]['t']
                 biprev = self._bi('%s.%d' % (pprev, 2 if tprev == 1 else 3))
                 L.call('b200sp_pw_dgrad', C.byref(dye), self._wq(p + '.0.0.weight'), skip.data_ptr() if skip is not None else None, 1.0,
-                       dprev.data_ptr(), self._bnbwd(cx, biprev, cx.Y['p%d' % (i - 1)], L.ACT_NONE), Mi, hid, cin, dt, sp)
+                       dprev.data_ptr(), self._bnbwd(cx, biprev, cx.Y['p%d' % (i - 1)], L.ACT_NONE), Mi, hid, cin, self.gemm_dtype, sp)
             else:
                 # block 1: depthwise reads the stem activation directly
                 y0, bi0 = cx.Y['stem'], self._bi('base.0.1')
@@ -396,7 +400,7 @@ class KRNEngine:
         hbuf = self._buf(cx.Y, 'dom_h', (B, h, w, 1280))
         fvt = self._vt_plain(cx.O[17])
         L.call('b200sp_pw_fwd', C.byref(fvt), self.store.w_ptr('domain_classifier.0.weight'),
-               self.store.w_ptr('domain_classifier.0.bias'), L.ACT_RELU, hbuf.data_ptr(), None, M, 1280, 320, dt, sp)
+               self.store.w_ptr('domain_classifier.0.bias'), L.ACT_RELU, hbuf.data_ptr(), None, M, 1280, 320, self.gemm_dtype, sp)
         L.call('b200sp_dann_head_fwd', hbuf.data_ptr(), self.store.w_ptr('domain_classifier.3.weight'),
                self.store.w_ptr('domain_classifier.3.bias'), cx.dom_pool.data_ptr(), cx.dom_z.data_ptr(), B, h * w, 1280, dt, sp)
         L.call('b200sp_bce_logits', cx.dom_z.data_ptr(), float(label), cx.dom_loss.data_ptr(), cx.dom_dz.data_ptr(), None, B, sp)
@@ -415,10 +419,10 @@ class KRNEngine:
                st.wg_ptr('domain_classifier.3.bias'), B, h * w, 1280, dt, sp)
         dvt = self._vt_plain(hbuf)                           # now holds dL/d(conv0 output)
         L.call('b200sp_pw_wgrad', C.byref(dvt), C.byref(self._vt_plain(cx.O[17])), st.wg_ptr('domain_classifier.0.weight'),
-               st.wg_ptr('domain_classifier.0.bias'), M, 1280, 320, dt, sp)
+               st.wg_ptr('domain_classifier.0.bias'), M, 1280, 320, self.gemm_dtype, sp)
         fg = self._buf(cx.dO, 'dom_f', cx.O[17].shape)
         L.call('b200sp_pw_dgrad', C.byref(dvt), st.w_ptr('domain_classifier.0.weight'), None, 1.0, fg.data_ptr(), None,
-               M, 1280, 320, dt, sp)
+               M, 1280, 320, self.gemm_dtype, sp)
         L.call('b200sp_scale_dev', fg.data_ptr(), fg.numel(), neg_alpha_dev.data_ptr(), 1.0, dt, sp)
         return fg
 
@@ -434,7 +438,7 @@ class KRNEngine:
         self._wgrad(C.byref(dyp), C.byref(dvt), self._wg(p + '.3.weight'), None, M, cout, cin, dt)
         gd = self._buf(cx.G, 'xd%d' % e, yd.shape)
         L.call('b200sp_pw_dgrad', C.byref(dyp), self._wq(p + '.3.weight'), None, 1.0, gd.data_ptr(),
-               self._bnbwd(cx, bid, yd, L.ACT_RELU), M, cout, cin, dt, sp)
+               self._bnbwd(cx, bid, yd, L.ACT_RELU), M, cout, cin, self.gemm_dtype, sp)
         dyd = self._vt_dy(cx, gd, yd, bid)
         L.call('b200sp_dw_bwd', C.byref(dyd), C.byref(in_vt), self._w(p + '.0.weight'), skip.data_ptr() if skip is not None else None,
                g_in.data_ptr(), self._wg(p + '.0.weight'), in_bn, B, h, w, cin, 1, dt, sp)

@@ -20,7 +20,17 @@ logger = logging.getLogger(__name__)
 
 
 def _dtype(cfg):
+    """storage dtype: fp32.  (B200SP_ENABLE_BF16=1 selects the experimental bf16-STORAGE engine instead)"""
     return L.BF16 if getattr(cfg, 'fp16', False) and L.BF16_ENABLED else L.F32
+
+
+def _tf32(cfg):
+    """`--use_fp16` (config.py:39; reference: torch.cuda.amp autocast + GradScaler, trainer.py:73-94) selects the mixed-precision
+    mode of this path: the 1x1-convolution GEMMs run SINGLE-pass TF32 on the tensor cores -- operands rounded to fp16's 10-bit
+    mantissa, fp32 exponent range, fp32 accumulation -- while storage, BatchNorm statistics, depthwise stencils, loss and the
+    optimizer stay fp32.  The exponent range is fp32's, so the reference's loss scaling has nothing to protect: the GradScaler
+    the CLI creates is accepted by the epoch loops and left at scale 1 (tests/test_krn_tf32_gpu.py)."""
+    return bool(getattr(cfg, 'fp16', False)) and not L.BF16_ENABLED
 
 
 def get_model(cfg):
@@ -29,8 +39,8 @@ def get_model(cfg):
     device = getattr(cfg, 'device', None)
     if not cfg.dann:
         if cfg.model_name == 'krn':
-            model = KeypointRegressionNet(cfg.num_keypoints, device=device, dtype=_dtype(cfg))
-            logger.info('KRN created')
+            model = KeypointRegressionNet(cfg.num_keypoints, device=device, dtype=_dtype(cfg), tf32_gemm=_tf32(cfg))
+            logger.info('KRN created' + (' (--use_fp16: single-pass TF32 GEMMs, fp32 storage)' if _tf32(cfg) else ''))
         else:
             from .spn import SpacecraftPoseNet
             model = SpacecraftPoseNet(cfg.num_classes, pretrain=True, device=device)

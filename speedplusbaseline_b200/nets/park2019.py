@@ -99,10 +99,10 @@ def default_init(store, seed=None, kaiming_prefixes=('base.', 'net.base.')):
 
 
 class KeypointRegressionNet(EngineModule):
-    def __init__(self, num_keypoints, device=None, dtype=L.F32, seed=None, _prefix='', _dann=False):
+    def __init__(self, num_keypoints, device=None, dtype=L.F32, seed=None, _prefix='', _dann=False, tf32_gemm=False):
         super().__init__()
         self.nK = num_keypoints
-        self.engine = KRNEngine(num_keypoints, prefix=_prefix, dann=_dann, device=device, dtype=dtype)
+        self.engine = KRNEngine(num_keypoints, prefix=_prefix, dann=_dann, device=device, dtype=dtype, tf32_gemm=tf32_gemm)
         self._register_store(self.engine.store, self.engine.key_order)
         default_init(self.engine.store, seed)
         if seed is None:

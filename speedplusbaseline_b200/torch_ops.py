@@ -133,6 +133,7 @@ _lib.define('bn_apply(Tensor y, Tensor scale, Tensor shift, Tensor? residual, in
 
 
 def bn_apply(y, scale, shift, residual, act):
+    """out = act(y*scale + shift) + residual  (the inverted-residual block output: no activation after the add)"""
     _chk(y, scale, shift, residual)
     Cc = y.shape[-1]
     out = torch.empty_like(y)

@@ -50,7 +50,7 @@ def test_depthwise_bn_reorg_loss(ops):
     sc, sh = torch.rand(32, generator=g) + 0.5, torch.randn(32, generator=g)
     res = torch.randn(2, 14, 14, 32, generator=g)
     out = ops.bn_apply(x.cuda(), sc.cuda(), sh.cuda(), res.cuda(), 1)
-    assert rel(out, torch.relu(x.double() * sc.double() + sh.double() + res.double())) < 1e-6
+    assert rel(out, torch.relu(x.double() * sc.double() + sh.double()) + res.double()) < 1e-6     # activation, THEN the residual (mobilenetv2.py:61-62)
     xr, x1 = torch.randn(2, 14, 14, 8, generator=g), torch.randn(2, 7, 7, 16, generator=g)
     cat = ops.reorg_cat(xr.cuda(), x1.cuda())
     t = xr.permute(0, 3, 1, 2)                                   # park2019.py:70-80 on NCHW
