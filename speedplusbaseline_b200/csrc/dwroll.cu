@@ -433,6 +433,8 @@ __global__ void __launch_bounds__(RNT, S == 2 ? 4 : 3) dwr_bwd2_kernel(const b20
                                                           const b200sp_bnbwd bn, const RGeom gm) {
     extern __shared__ __align__(16) unsigned char bwd2_smem[];
     Bwd2Shared& sh = *reinterpret_cast<Bwd2Shared*>(bwd2_smem);
+    pdl_trigger();          // programmatic dependent launch (common.cuh): block scheduling overlapped the predecessor's tail
+    pdl_wait();
     const int tid = threadIdx.x;
     const int cl = tid % gm.CB, sl = tid / gm.CB;
     const int cbase = blockIdx.y * gm.CB * 4;
@@ -616,6 +618,8 @@ __global__ void __launch_bounds__(RNT, S == 2 ? 4 : 3) dwr_fwd2_kernel(const b20
     constexpr int OW = S == 1 ? 4 : 2;
     constexpr int NC = (OW - 1) * S + 3;
     __shared__ Fwd2Shared sh;
+    pdl_trigger();
+    pdl_wait();
     const int tid = threadIdx.x;
     const int cl = tid % gm.CB, sl = tid / gm.CB;
     const int cbase = blockIdx.y * gm.CB * 4;
@@ -749,11 +753,11 @@ int launch_fwd(const b200sp_vtensor* x, const float* w9c, void* y, const b200sp_
         (long long)B * H * W * C < (1ll << 31)) {
         const bool r6 = x->act == B200SP_ACT_RELU6;
         if (stride == 1) {
-            if (r6) dwr_fwd2_kernel<1, B200SP_ACT_RELU6><<<grid, RNT, 0, st>>>(*x, w9c, (float*)y, b, gm);
-            else    dwr_fwd2_kernel<1, B200SP_ACT_RELU><<<grid, RNT, 0, st>>>(*x, w9c, (float*)y, b, gm);
+            if (r6) b200sp_launch_pdl(dwr_fwd2_kernel<1, B200SP_ACT_RELU6>, grid, dim3(RNT), 0, st, *x, w9c, (float*)y, b, gm);
+            else    b200sp_launch_pdl(dwr_fwd2_kernel<1, B200SP_ACT_RELU>, grid, dim3(RNT), 0, st, *x, w9c, (float*)y, b, gm);
         } else {
-            if (r6) dwr_fwd2_kernel<2, B200SP_ACT_RELU6><<<grid, RNT, 0, st>>>(*x, w9c, (float*)y, b, gm);
-            else    dwr_fwd2_kernel<2, B200SP_ACT_RELU><<<grid, RNT, 0, st>>>(*x, w9c, (float*)y, b, gm);
+            if (r6) b200sp_launch_pdl(dwr_fwd2_kernel<2, B200SP_ACT_RELU6>, grid, dim3(RNT), 0, st, *x, w9c, (float*)y, b, gm);
+            else    b200sp_launch_pdl(dwr_fwd2_kernel<2, B200SP_ACT_RELU>, grid, dim3(RNT), 0, st, *x, w9c, (float*)y, b, gm);
         }
         B200SP_COUNT_LAUNCH();
         B200SP_RETURN_LAST();
@@ -794,11 +798,11 @@ int launch_bwd(const b200sp_vtensor* dy, const b200sp_vtensor* x, const float* w
         }
         const bool r6 = bn->act == B200SP_ACT_RELU6;
         if (stride == 1) {
-            if (r6) dwr_bwd2_kernel<1, B200SP_ACT_RELU6><<<grid, RNT, smem, st>>>(*dy, w9c, (float*)g_in, dw9c, b, gm);
-            else    dwr_bwd2_kernel<1, B200SP_ACT_RELU><<<grid, RNT, smem, st>>>(*dy, w9c, (float*)g_in, dw9c, b, gm);
+            if (r6) b200sp_launch_pdl(dwr_bwd2_kernel<1, B200SP_ACT_RELU6>, grid, dim3(RNT), smem, st, *dy, w9c, (float*)g_in, dw9c, b, gm);
+            else    b200sp_launch_pdl(dwr_bwd2_kernel<1, B200SP_ACT_RELU>, grid, dim3(RNT), smem, st, *dy, w9c, (float*)g_in, dw9c, b, gm);
         } else {
-            if (r6) dwr_bwd2_kernel<2, B200SP_ACT_RELU6><<<grid, RNT, smem, st>>>(*dy, w9c, (float*)g_in, dw9c, b, gm);
-            else    dwr_bwd2_kernel<2, B200SP_ACT_RELU><<<grid, RNT, smem, st>>>(*dy, w9c, (float*)g_in, dw9c, b, gm);
+            if (r6) b200sp_launch_pdl(dwr_bwd2_kernel<2, B200SP_ACT_RELU6>, grid, dim3(RNT), smem, st, *dy, w9c, (float*)g_in, dw9c, b, gm);
+            else    b200sp_launch_pdl(dwr_bwd2_kernel<2, B200SP_ACT_RELU>, grid, dim3(RNT), smem, st, *dy, w9c, (float*)g_in, dw9c, b, gm);
         }
         B200SP_COUNT_LAUNCH();
         B200SP_RETURN_LAST();

@@ -11,6 +11,8 @@ template <typename T>
 __global__ void __launch_bounds__(EW_NT) bn_apply_kernel(const T* __restrict__ y, const float* __restrict__ scale,
                                                          const float* __restrict__ shift, const T* __restrict__ res,
                                                          int act, T* __restrict__ out, long long n4, int C4) {
+    pdl_trigger();
+    pdl_wait();
     for (long long i = (long long)blockIdx.x * EW_NT + threadIdx.x; i < n4; i += (long long)gridDim.x * EW_NT) {
         const int c = (int)(i % C4) * 4;
         float4 v = Vec4<T>::ld(y + i * 4);
@@ -298,8 +300,8 @@ extern "C" int b200sp_bn_apply(const void* y, const float* scale, const float* s
     if (C % 4) return B200SP_EINVAL;
     const long long n4 = M * (C / 4);
     if (dtype == B200SP_F32)
-        bn_apply_kernel<float><<<ew_grid(n4), EW_NT, 0, (cudaStream_t)stream>>>((const float*)y, scale, shift, (const float*)residual,
-                                                                              act, (float*)out, n4, C / 4);
+        b200sp_launch_pdl(bn_apply_kernel<float>, dim3(ew_grid(n4)), dim3(EW_NT), 0, (cudaStream_t)stream, (const float*)y, scale, shift,
+                          (const float*)residual, act, (float*)out, n4, C / 4);
     else
         bn_apply_kernel<bf16><<<ew_grid(n4), EW_NT, 0, (cudaStream_t)stream>>>((const bf16*)y, scale, shift, (const bf16*)residual,
                                                                              act, (bf16*)out, n4, C / 4);

@@ -57,7 +57,7 @@ struct alignas(64) Tcg2Args {
     int nm;                          // operand copies per tile: 2 = (tf32 hi, lo) for 3xTF32, 1 = single-pass TF32 (--use_fp16 mode)
     int b_res;
     int ac_last, nks_last;
-    int b_atoms;                     // MN-major B: 128-byte atoms per tile
+    int a_atoms, b_atoms;            // MN-major operands: 128-byte atoms per tile that hold data (A: min(P, 128) columns)
     uint32_t a_tx, b_tx;             // TMA bytes per k-block of one A tensor / of B
     uint32_t off_bres;
     uint32_t a_op_bytes, b_op_bytes;
@@ -336,8 +336,8 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
                 const uint32_t rbase = s_base + g.off_raw + rs * g.raw_stage_bytes;
                 const uint32_t bar = tc::smem_u32(&rawfull[rs]);
                 tc::mbar_arrive_expect_tx(&rawfull[rs], tx);
-                tma_operand<ALAY>(rbase, &g.mapA, bar, f.w.p0, f.kb, BM / 32);
-                if (AMODE == XM_DY) tma_operand<ALAY>(rbase + slotA2 * 8192, &g.mapA2, bar, f.w.p0, f.kb, BM / 32);
+                tma_operand<ALAY>(rbase, &g.mapA, bar, f.w.p0, f.kb, g.a_atoms);
+                if (AMODE == XM_DY) tma_operand<ALAY>(rbase + slotA2 * 8192, &g.mapA2, bar, f.w.p0, f.kb, g.a_atoms);
                 if (!g.b_res) tma_operand<BLAY>(rbase + slotB * 8192, &g.mapB, bar, f.w.q0, f.kb, g.b_atoms);
                 if (++rs == g.n_raw) { rs = 0; par ^= 1; }
                 f.next(g);
@@ -355,7 +355,9 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
         const bool poller = (pg >> 5) == 0;                      // first warp of the group polls the mbarriers
         Conv<ALAY, AMODE> CA;
         Conv<BLAY, BMODE> CB;
-        CA.init(g.a, g.P, g.R, g.nkb, g.ac_last, pg, GT, BM);
+        // MN-major A (weight gradient): only the atoms that hold columns of the operand are fetched and converted -- the MMA still
+        // spans 128 accumulator rows, the rest read stale shared memory and produce rows the epilogue never stores
+        CA.init(g.a, g.P, g.R, g.nkb, g.ac_last, pg, GT, ALAY == TCG_LAY_KM ? BM : g.a_atoms * 32);
         CB.init(g.b, g.Q, g.R, g.nkb, g.ac_last, pg, GT, g.BN);
         CA.single = CB.single = g.nm == 1;
         const uint32_t raw0 = s_base + g.off_raw + pg * 16;
@@ -742,6 +744,7 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st) {
     }
     const int numPt = ceil_div(a.P, BM);
     a.nkb = ceil_div(a.R, E::KE);
+    a.a_atoms = a.P >= BM ? BM / 32 : ceil_div(a.P, 32);
     {
         const int rem = a.R - (a.nkb - 1) * E::KE;
         a.nks_last = ceil_div(rem, 2 * E::EPV);
@@ -779,7 +782,9 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st) {
         // measured (profiles/r2_gemm_groups.txt): 2 groups are worth ~4 % on the long-M data-gradient shapes, 4 bring nothing
         // more (the MMA issue thread becomes the critical path), and the MN-major weight-gradient form is fastest with one
         if (gmax < 0) { const char* e = getenv("B200SP_TCG2_GROUPS"); gmax = e ? atoi(e) : 2; if (gmax != 1 && gmax != 2 && gmax != 4) gmax = 2; }
-        int G = EPI == TCG_EPI_ATOMIC ? 1 : gmax;
+        static int gwg = -1;
+        if (gwg < 0) { const char* e = getenv("B200SP_TCG2_WGRAD_GROUPS"); gwg = e ? atoi(e) : 1; if (gwg != 1 && gwg != 2 && gwg != 4) gwg = 1; }
+        int G = EPI == TCG_EPI_ATOMIC ? gwg : gmax;
         while (G > 1 && !fit(G, G)) G >>= 1;
         if (G == 1) { a.n_op = 2; a.n_raw = 2; } else { a.n_op = G; a.n_raw = G; }
         a.groups = G;
@@ -816,7 +821,7 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st) {
     // ---- tensor maps of the raw operands ----
     int rc;
     if (ALAY == TCG_LAY_KM) { rc = encode_f32(&a.mapA, a.a.x, a.R, a.P, a.lda, BM); a.a_tx = BM * 128; }
-    else                    { rc = encode_f32(&a.mapA, a.a.x, a.P, a.R, a.lda, 32); a.a_tx = (BM / 32) * 4096; }
+    else                    { rc = encode_f32(&a.mapA, a.a.x, a.P, a.R, a.lda, 32); a.a_tx = a.a_atoms * 4096; }
     if (rc) return rc;
     if (AMODE == XM_DY) {
         rc = ALAY == TCG_LAY_KM ? encode_f32(&a.mapA2, a.a.x2, a.R, a.P, a.lda, BM) : encode_f32(&a.mapA2, a.a.x2, a.P, a.R, a.lda, 32);
