@@ -463,6 +463,63 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
     if (tg + 24 < 27) atomicAdd(dw + n * 27 + tg + 24, acc[3]);
 }
 
+// Second generation of the stem weight gradient (round 2; the first took 199 us = 0.14 of the copy peak because every one of
+// the 27 x 64 staged input taps cost a div/mod chain and an uncoalesced scalar load).  One CTA iteration = one output row of one
+// image: the 3 x 3 input rows it needs are loaded ONCE with coalesced 16-byte loads (zero rows / the left zero column stand in
+// for the padding), the transformed gradient row likewise, and every thread then owns dW[n][tap], tap = tg + 8 j, j < 4, with
+// the gradient read conflict-free (consecutive n) and the input broadcast (one address per warp).
+constexpr int SW_XP = 232;                      // padded row pitch of the staged input rows (225 used: column wi + 1)
+template <typename T>
+__global__ void __launch_bounds__(256) stem_wgrad2_kernel(const float* __restrict__ x, const b200sp_vtensor dy, float* __restrict__ dw,
+                                                          int B, int H, int W, int Ho, int Wo) {
+    extern __shared__ __align__(16) float sw_smem[];
+    float* s_x = sw_smem;                        // [3 ci][3 kh][SW_XP]
+    float* s_dy = sw_smem + 9 * SW_XP;           // [Wo][32]
+    const int tid = threadIdx.x;
+    const int n = tid & 31, tg = tid >> 5;
+    int xo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int t = min(tg + 8 * j, 26);
+        xo[j] = ((t / 9) * 3 + (t % 9) / 3) * SW_XP + (t % 3);      // + 2*wo: column (2 wo - 1 + kw) + 1
+    }
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = tid; i < 9; i += 256) s_x[i * SW_XP] = 0.f;       // the zero column left of the image (wi = -1)
+    const int W4 = W >> 2, nrow = B * Ho;
+    for (int r = blockIdx.x; r < nrow; r += gridDim.x) {
+        const int b = r / Ho, ho = r - b * Ho;
+        __syncthreads();                                             // previous row fully consumed
+        for (int i = tid; i < 9 * W4; i += 256) {
+            const int row = i / W4, c4 = (i - row * W4) * 4;
+            const int ci = row / 3, hi = 2 * ho - 1 + (row - ci * 3);
+            float4 v = f4zero();
+            if (hi >= 0 && hi < H) v = __ldg(reinterpret_cast<const float4*>(x + ((size_t)(b * 3 + ci) * H + hi) * W + c4));
+            float* d = s_x + row * SW_XP + 1 + c4;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+        const size_t prow = (size_t)r * Wo * STEM_C;
+        for (int i = tid; i < Wo * (STEM_C / 4); i += 256) {
+            const int c4 = (i & (STEM_C / 4 - 1)) * 4;
+            const float4 v = vt_load4<T>(dy, prow + (size_t)i * 4, c4);
+            *reinterpret_cast<float4*>(s_dy + i * 4) = v;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int p = 0; p < Wo; ++p) {
+            const float d = s_dy[p * STEM_C + n];
+            const float* xr = s_x + 2 * p;
+            acc[0] = fmaf(d, xr[xo[0]], acc[0]);
+            acc[1] = fmaf(d, xr[xo[1]], acc[1]);
+            acc[2] = fmaf(d, xr[xo[2]], acc[2]);
+            acc[3] = fmaf(d, xr[xo[3]], acc[3]);
+        }
+    }
+    atomicAdd(dw + n * 27 + tg, acc[0]);
+    atomicAdd(dw + n * 27 + tg + 8, acc[1]);
+    atomicAdd(dw + n * 27 + tg + 16, acc[2]);
+    if (tg + 24 < 27) atomicAdd(dw + n * 27 + tg + 24, acc[3]);
+}
+
 }  // namespace
 
 int dw_fwd_legacy(const b200sp_vtensor* x, const float* w9c, void* y, const b200sp_bnfwd* bn,
@@ -518,6 +575,15 @@ extern "C" int b200sp_stem_wgrad(const float* x_nchw, const b200sp_vtensor* dy, 
     const long long npix = (long long)B * Ho * Wo;
     int grid = (int)((npix + 63) / 64);
     if (grid > NUM_SMS * 8) grid = NUM_SMS * 8;
+    static int v2 = -1;
+    if (v2 < 0) { const char* e = getenv("B200SP_STEM_WGRAD"); v2 = (e && e[0] == '1') ? 0 : 1; }
+    if (v2 && dtype == B200SP_F32 && W % 4 == 0 && W + 1 <= SW_XP && ((uintptr_t)x_nchw & 15) == 0) {
+        const size_t smem = sizeof(float) * (9 * SW_XP + (size_t)Wo * STEM_C);
+        int g2 = B * Ho < NUM_SMS * 4 ? B * Ho : NUM_SMS * 4;
+        stem_wgrad2_kernel<float><<<g2, 256, smem, (cudaStream_t)stream>>>(x_nchw, *dy, dw, B, H, W, Ho, Wo);
+        B200SP_COUNT_LAUNCH();
+        B200SP_RETURN_LAST();
+    }
     if (dtype == B200SP_F32) stem_wgrad_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, *dy, dw, B, H, W, Ho, Wo);
     else stem_wgrad_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, *dy, dw, B, H, W, Ho, Wo);
     B200SP_COUNT_LAUNCH();

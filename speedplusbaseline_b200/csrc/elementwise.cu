@@ -154,6 +154,56 @@ __global__ void __launch_bounds__(EW_NT) reorg_cat_bwd_kernel(const T* __restric
 
 // ---- KRN head: logits[b,n] += sum_k a[b,k] * W[n,k],  k = (h*W + w)*C + c ---------------------
 constexpr int HEAD_MAXN = 24;
+// Second generation of the head forward (round 2; the first spent 72 us on 5-step shuffle reductions per (image, output)).
+// One CTA = a 128-wide slice of the 50176-long reduction: the activated inputs [B][128] and the weights [N][128] of the slice
+// are staged once (16-byte loads), then thread o owns logits (b, n) = (o / N, o % N), o += 256, as a 128-long dot product
+// read from shared memory in 16-byte pieces (row pitch 132 floats: 8 consecutive rows cover all banks), one atomicAdd each.
+constexpr int HF_KC = 128, HF_LD = HF_KC + 4, HF_MAXB = 64;
+template <typename T>
+__global__ void __launch_bounds__(EW_NT) head_fwd2_kernel(const b200sp_vtensor x, const float* __restrict__ w, float* __restrict__ logits,
+                                                          int B, int HWC, int C, int N) {
+    extern __shared__ __align__(16) float hf_smem[];
+    float* s_x = hf_smem;                       // [B][HF_LD]
+    float* s_w = hf_smem + (size_t)B * HF_LD;   // [N][HF_LD]
+    const int tid = threadIdx.x;
+    const int k0 = blockIdx.x * HF_KC;
+    const ActP ap = act_params(x.act);
+    for (int i = tid; i < B * (HF_KC / 4); i += EW_NT) {
+        const int b = i / (HF_KC / 4), k4 = (i - b * (HF_KC / 4)) * 4, k = k0 + k4;
+        float4 v = f4zero();
+        if (k < HWC) {
+            v = Vec4<T>::ld(reinterpret_cast<const T*>(x.x) + (size_t)b * HWC + k);
+            if (x.mode == B200SP_VT_BNACT) {
+                const int c = k % C;
+                const float4 sc = ldg4(x.p0 + c), sh = ldg4(x.p1 + c);
+                v = make_float4(act_fwd(fmaf(v.x, sc.x, sh.x), ap), act_fwd(fmaf(v.y, sc.y, sh.y), ap),
+                                act_fwd(fmaf(v.z, sc.z, sh.z), ap), act_fwd(fmaf(v.w, sc.w, sh.w), ap));
+            }
+        }
+        *reinterpret_cast<float4*>(s_x + b * HF_LD + k4) = v;
+    }
+    for (int i = tid; i < N * (HF_KC / 4); i += EW_NT) {
+        const int n = i / (HF_KC / 4), k4 = (i - n * (HF_KC / 4)) * 4, k = k0 + k4;
+        float4 v = f4zero();
+        if (k < HWC) v = ldg4(w + (size_t)n * HWC + k);
+        *reinterpret_cast<float4*>(s_w + n * HF_LD + k4) = v;
+    }
+    __syncthreads();
+    for (int o = tid; o < B * N; o += EW_NT) {
+        const int b = o / N, n = o - b * N;
+        const float4* xr = reinterpret_cast<const float4*>(s_x + b * HF_LD);
+        const float4* wr = reinterpret_cast<const float4*>(s_w + n * HF_LD);
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
+        for (int j = 0; j < HF_KC / 4; ++j) {
+            const float4 xv = xr[j], wv = wr[j];
+            a0 = fmaf(xv.x, wv.x, a0); a1 = fmaf(xv.y, wv.y, a1);
+            a0 = fmaf(xv.z, wv.z, a0); a1 = fmaf(xv.w, wv.w, a1);
+        }
+        atomicAdd(logits + o, a0 + a1);
+    }
+}
+
 constexpr int HEAD_BT = 8;       // batch rows per smem pass
 template <typename T>
 __global__ void __launch_bounds__(EW_NT) head_fwd_kernel(const b200sp_vtensor x, const float* __restrict__ w, float* __restrict__ logits,
@@ -394,6 +444,19 @@ extern "C" int b200sp_head_fwd(const b200sp_vtensor* x, const float* w, float* l
                                int B, int HWC, int C, int N, int dtype, void* stream) {
     if (dtype != B200SP_F32 && dtype != B200SP_BF16) return B200SP_ENOSYS;
     if (N > HEAD_MAXN || x->mode == B200SP_VT_DY) return B200SP_EINVAL;
+    if (dtype == B200SP_F32 && B <= HF_MAXB && HWC % 4 == 0 && C % 4 == 0 && x->act != B200SP_ACT_SIGMOID &&
+        (((uintptr_t)x->x | (uintptr_t)w) & 15) == 0) {
+        const size_t smem = sizeof(float) * (size_t)(B + N) * HF_LD;
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(head_fwd2_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * (HF_MAXB + HEAD_MAXN) * HF_LD));
+            if (e != cudaSuccess) return (int)e;
+            attr_set = true;
+        }
+        head_fwd2_kernel<float><<<ceil_div(HWC, HF_KC), EW_NT, smem, (cudaStream_t)stream>>>(*x, w, logits, B, HWC, C, N);
+        B200SP_COUNT_LAUNCH();
+        B200SP_RETURN_LAST();
+    }
     if (dtype == B200SP_F32) head_fwd_kernel<float><<<ceil_div(HWC, EW_NT), EW_NT, 0, (cudaStream_t)stream>>>(*x, w, logits, B, HWC, C, N);
     else head_fwd_kernel<bf16><<<ceil_div(HWC, EW_NT), EW_NT, 0, (cudaStream_t)stream>>>(*x, w, logits, B, HWC, C, N);
     B200SP_COUNT_LAUNCH();

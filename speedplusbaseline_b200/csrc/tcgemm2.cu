@@ -363,9 +363,11 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
         const uint32_t raw0 = s_base + g.off_raw + pg * 16;
         int n = gi;                                              // sequence number of the k-block this group converts next
         const int nb = g.b_res ? g.nkb : 0;
+        // ring positions advance by G per iteration and wrap at most once (every ring depth is a multiple of G >= G): no
+        // divisions in the loop -- they cost as much as the conversion itself (r2l: +35 % on the weight-gradient shapes)
+        int rs = gi % g.n_raw;
+        uint32_t rpar = (uint32_t)(gi / g.n_raw) & 1u;
         for (; n < nb; n += G) {
-            const int rs = n % g.n_raw;
-            const uint32_t rpar = (uint32_t)(n / g.n_raw) & 1u;
             if (poller) mbar_wait_guard(&rawfull[rs], rpar);
             named_bar(2 + gi, GT);
             tc::mbar_try_wait(&rawfull[rs], rpar);              // completes at once: every thread observes the TMA phase itself
@@ -374,6 +376,8 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
             CB.convert(n, 0, raw0 + rs * g.raw_stage_bytes, 0, b_hi, b_lo);
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&rawempty[rs]);
+            rs += G;
+            if (rs >= g.n_raw) { rs -= g.n_raw; rpar ^= 1u; }
         }
         if (g.b_res) {
             tc::fence_proxy_async_smem();
@@ -383,10 +387,10 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
         KIter cons;
         cons.init(g, blockIdx.x, total, gridDim.x);
         for (int sk = nb; sk < n && cons.valid(); ++sk) cons.next(g);       // this group's first item
+        int os = (n - nb) % g.n_op;
+        uint32_t opar = ((uint32_t)((n - nb) / g.n_op) & 1u) ^ 1u;
         int tlc = 0;
         while (cons.valid()) {
-            const int rs = n % g.n_raw, m = n - nb, os = m % g.n_op;
-            const uint32_t rpar = (uint32_t)(n / g.n_raw) & 1u, opar = ((uint32_t)(m / g.n_op) & 1u) ^ 1u;
             CA.load_params(cons.kb);
             if (!g.b_res) CB.load_params(cons.kb);
             if (pt == 0) TL(2, tlc);
@@ -408,8 +412,12 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
             if (lane == 0) { tc::mbar_arrive(&full[os]); tc::mbar_arrive(&rawempty[rs]); }
             if (pt == 0) TL(5, tlc);
             ++tlc;
-            n += G;
-            for (int sk = 0; sk < G && cons.valid(); ++sk) cons.next(g);
+            rs += G;
+            if (rs >= g.n_raw) { rs -= g.n_raw; rpar ^= 1u; }
+            os += G;
+            if (os >= g.n_op) { os -= g.n_op; opar ^= 1u; }
+            if (G == 1) cons.next(g);
+            else for (int sk = 0; sk < G && cons.valid(); ++sk) cons.next(g);
         }
     } else if (warp == MMA_WARP) {
         // ======================================= MMA ISSUER ======================================
