@@ -226,7 +226,7 @@ def secondary_workloads(dev, stepper, d_img, d_tgt, k=8):
     spn.engine.store.params.normal_(0.0, 0.01)                     # random init on the device (152 M parameters)
     spn.train()
     opt = FusedAdamW(spn._store, spn.parameters(), lr=1e-3, weight_decay=0.01, clip_mode=2)
-    ss = SPNTrainStep(spn, opt, use_graph=False)
+    ss = SPNTrainStep(spn, opt)            # CUDA-graph step: the dropout masks come from a device-resident counter
     x = torch.rand(32, 3, 227, 227, device=dev)
     yc = torch.zeros(32, 5000, device=dev)
     yc[:, :5] = 0.2

@@ -476,14 +476,20 @@ __global__ void __launch_bounds__(256) stem_wgrad2_kernel(const float* __restric
     float* s_x = sw_smem;                        // [3 ci][3 kh][SW_XP]
     float* s_dy = sw_smem + 9 * SW_XP;           // [Wo][32]
     const int tid = threadIdx.x;
-    const int n = tid & 31, tg = tid >> 5;
+    // register tile: 4 output channels x 4 taps per thread (5 shared-memory loads per 16 FMAs -- the first cut of this kernel,
+    // 1 channel x 4 taps, was bound by its 5 loads per 4 FMAs); 4 pixel groups of 64 threads share a row
+    const int grp = tid >> 6, l = tid & 63, nb = l & 7, tb = l >> 3;
     int xo[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const int t = min(tg + 8 * j, 26);
+        const int t = min(tb * 4 + j, 26);
         xo[j] = ((t / 9) * 3 + (t % 9) / 3) * SW_XP + (t % 3);      // + 2*wo: column (2 wo - 1 + kw) + 1
     }
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     for (int i = tid; i < 9; i += 256) s_x[i * SW_XP] = 0.f;       // the zero column left of the image (wi = -1)
     const int W4 = W >> 2, nrow = B * Ho;
     for (int r = blockIdx.x; r < nrow; r += gridDim.x) {
@@ -504,20 +510,34 @@ __global__ void __launch_bounds__(256) stem_wgrad2_kernel(const float* __restric
             *reinterpret_cast<float4*>(s_dy + i * 4) = v;
         }
         __syncthreads();
-#pragma unroll 4
-        for (int p = 0; p < Wo; ++p) {
-            const float d = s_dy[p * STEM_C + n];
-            const float* xr = s_x + 2 * p;
-            acc[0] = fmaf(d, xr[xo[0]], acc[0]);
-            acc[1] = fmaf(d, xr[xo[1]], acc[1]);
-            acc[2] = fmaf(d, xr[xo[2]], acc[2]);
-            acc[3] = fmaf(d, xr[xo[3]], acc[3]);
+        if (tb < 7) {
+#pragma unroll 2
+            for (int p = grp; p < Wo; p += 4) {
+                const float4 d = *reinterpret_cast<const float4*>(s_dy + p * STEM_C + nb * 4);
+                const float* xr = s_x + 2 * p;
+                const float x0 = xr[xo[0]], x1 = xr[xo[1]], x2 = xr[xo[2]], x3 = xr[xo[3]];
+                acc[0][0] = fmaf(d.x, x0, acc[0][0]); acc[0][1] = fmaf(d.x, x1, acc[0][1]); acc[0][2] = fmaf(d.x, x2, acc[0][2]); acc[0][3] = fmaf(d.x, x3, acc[0][3]);
+                acc[1][0] = fmaf(d.y, x0, acc[1][0]); acc[1][1] = fmaf(d.y, x1, acc[1][1]); acc[1][2] = fmaf(d.y, x2, acc[1][2]); acc[1][3] = fmaf(d.y, x3, acc[1][3]);
+                acc[2][0] = fmaf(d.z, x0, acc[2][0]); acc[2][1] = fmaf(d.z, x1, acc[2][1]); acc[2][2] = fmaf(d.z, x2, acc[2][2]); acc[2][3] = fmaf(d.z, x3, acc[2][3]);
+                acc[3][0] = fmaf(d.w, x0, acc[3][0]); acc[3][1] = fmaf(d.w, x1, acc[3][1]); acc[3][2] = fmaf(d.w, x2, acc[3][2]); acc[3][3] = fmaf(d.w, x3, acc[3][3]);
+            }
         }
     }
-    atomicAdd(dw + n * 27 + tg, acc[0]);
-    atomicAdd(dw + n * 27 + tg + 8, acc[1]);
-    atomicAdd(dw + n * 27 + tg + 16, acc[2]);
-    if (tg + 24 < 27) atomicAdd(dw + n * 27 + tg + 24, acc[3]);
+    // reduce the four pixel groups in shared memory, then one atomic per weight and CTA
+    __syncthreads();
+    float* s_red = s_dy;                         // [4 groups][32 x 28]   (Wo*32 >= 4*896 floats is checked by the launcher)
+    if (tb < 7) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s_red[grp * 896 + (nb * 4 + i) * 28 + tb * 4 + j] = acc[i][j];
+    }
+    __syncthreads();
+    for (int o = tid; o < 32 * 27; o += 256) {
+        const int n = o / 27, t = o - n * 27;
+        const int q = n * 28 + t;
+        atomicAdd(dw + o, s_red[q] + s_red[896 + q] + s_red[2 * 896 + q] + s_red[3 * 896 + q]);
+    }
 }
 
 }  // namespace
@@ -577,7 +597,7 @@ extern "C" int b200sp_stem_wgrad(const float* x_nchw, const b200sp_vtensor* dy, 
     if (grid > NUM_SMS * 8) grid = NUM_SMS * 8;
     static int v2 = -1;
     if (v2 < 0) { const char* e = getenv("B200SP_STEM_WGRAD"); v2 = (e && e[0] == '1') ? 0 : 1; }
-    if (v2 && dtype == B200SP_F32 && W % 4 == 0 && W + 1 <= SW_XP && ((uintptr_t)x_nchw & 15) == 0) {
+    if (v2 && dtype == B200SP_F32 && W % 4 == 0 && W + 1 <= SW_XP && Wo * STEM_C >= 4 * 896 && ((uintptr_t)x_nchw & 15) == 0) {
         const size_t smem = sizeof(float) * (9 * SW_XP + (size_t)Wo * STEM_C);
         int g2 = B * Ho < NUM_SMS * 4 ? B * Ho : NUM_SMS * 4;
         stem_wgrad2_kernel<float><<<g2, 256, smem, (cudaStream_t)stream>>>(x_nchw, *dy, dw, B, H, W, Ho, Wo);

@@ -21,6 +21,9 @@ int dw_bwd_legacy(const b200sp_vtensor* dy, const b200sp_vtensor* x, const float
 namespace {
 
 constexpr int RNT = 128;          // threads per CTA
+#ifndef DWR_S1_OCC
+#define DWR_S1_OCC 3                // resident CTAs per SM requested for the stride-1 second-generation kernels (register cap 168)
+#endif
 constexpr int MAXCB = 32;         // channel quads per CTA row
 
 struct RGeom {
@@ -428,7 +431,7 @@ __device__ __forceinline__ float4 bwd2_finish(float4 dg, float4 yin, float4 z, f
 }
 
 template <int S, int ACT>
-__global__ void __launch_bounds__(RNT, S == 2 ? 4 : 3) dwr_bwd2_kernel(const b200sp_vtensor dy, const float* __restrict__ w9c,
+__global__ void __launch_bounds__(RNT, S == 2 ? 4 : DWR_S1_OCC) dwr_bwd2_kernel(const b200sp_vtensor dy, const float* __restrict__ w9c,
                                                           float* __restrict__ g_in, float* __restrict__ dw9c,
                                                           const b200sp_bnbwd bn, const RGeom gm) {
     extern __shared__ __align__(16) unsigned char bwd2_smem[];
@@ -613,7 +616,7 @@ struct Fwd2Shared {
 };
 
 template <int S, int ACT>
-__global__ void __launch_bounds__(RNT, S == 2 ? 4 : 3) dwr_fwd2_kernel(const b200sp_vtensor x, const float* __restrict__ w9c,
+__global__ void __launch_bounds__(RNT, S == 2 ? 4 : DWR_S1_OCC) dwr_fwd2_kernel(const b200sp_vtensor x, const float* __restrict__ w9c,
                                                                        float* __restrict__ y, const b200sp_bnfwd bn, const RGeom gm) {
     constexpr int OW = S == 1 ? 4 : 2;
     constexpr int NC = (OW - 1) * S + 3;
