@@ -185,7 +185,7 @@ __device__ __forceinline__ void split_store(float4 v, uint32_t dst_hi, uint32_t 
 // The operand tile uses the same (atom, row, chunk) with the UMMA swizzle applied to the chunk index.  A converter GROUP of
 // GT threads (GT = 512 / groups, a multiple of 128) deals the pieces q = pg + i*GT: the chunk index and the swizzle phase of
 // a thread's pieces never change (GT/8 rows is a multiple of 8), so source and destination both advance by GT*16 bytes.
-template <int LAY, int MODE>
+template <int LAY, int MODE, bool GRP>
 struct Conv {
     b200sp_vtensor vt;
     ActP act;
@@ -238,11 +238,11 @@ struct Conv {
     // raw / raw2: this thread's piece 0 in the raw stage (stage base + operand offset + pg*16); op_hi / op_lo: operand tile bases
     __device__ __forceinline__ void convert(int kb, int mn0, uint32_t raw, uint32_t raw2, uint32_t op_hi, uint32_t op_lo) {
         if (LAY == TCG_LAY_KM && kb == nkb - 1 && gc >= ac_last) return;      // partial last k-block: the MMA never reads these chunks
-        if (GT == PROD_T) {                 // one group: at most APT pieces per thread, fully unrolled (independent lds / sts chains)
+        if (!GRP || GT == PROD_T) {         // one group: at most APT pieces per thread, fully unrolled (independent lds / sts chains)
 #pragma unroll
             for (int i = 0; i < APT; ++i)
                 if (pg + i * PROD_T < npieces) piece(kb, mn0, pg + i * PROD_T, (uint32_t)i * (PROD_T * 16), raw, raw2, op_hi, op_lo);
-        } else {
+        } else if (GRP) {
             const uint32_t step = (uint32_t)GT * 16u;
             uint32_t o = 0;
 #pragma unroll 2
@@ -262,7 +262,7 @@ __device__ __forceinline__ void tma_operand(uint32_t dst, const CUtensorMap* m, 
 }
 
 // =====================================================================================================
-template <int ALAY, int BLAY, int EPI, int AMODE, int BMODE>
+template <int ALAY, int BLAY, int EPI, int AMODE, int BMODE, bool GRP>
 __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ Tcg2Args g) {
     using T = float;
     using E = ETf;
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
     const int total = g.numPt * g.numQt * g.splits;
 
     if (tid == 0) {
-        const int gw = PROD_T / 32 / g.groups;                 // warps per converter group
+        const int gw = PROD_T / 32 / (GRP ? g.groups : 1);     // warps per converter group
         for (int i = 0; i < MAX_OP; ++i) { tc::mbar_init(&full[i], gw); tc::mbar_init(&empty[i], 1); }
         for (int i = 0; i < 4; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], g.split_epi ? EPI_W / EPI_SETS : EPI_W); }
         tc::mbar_init(bfull, PROD_T / 32);
@@ -350,11 +350,11 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
         // what hides the lds -> ALU -> sts -> proxy fence -> arrive latency chain (~1300 cycles per k-block, r2f timelines).
         // n_raw and n_op are multiples of `groups`, so a ring slot is always filled by the same group (single-producer phases).
         const int pt = tid - PROD_TID0;
-        const int G = g.groups, GT = PROD_T / G;
+        const int G = GRP ? g.groups : 1, GT = GRP ? PROD_T / G : PROD_T;       // GRP == false: one group, everything below folds to constants
         const int gi = pt / GT, pg = pt - gi * GT;
         const bool poller = (pg >> 5) == 0;                      // first warp of the group polls the mbarriers
-        Conv<ALAY, AMODE> CA;
-        Conv<BLAY, BMODE> CB;
+        Conv<ALAY, AMODE, GRP> CA;
+        Conv<BLAY, BMODE, GRP> CB;
         // MN-major A (weight gradient): only the atoms that hold columns of the operand are fetched and converted -- the MMA still
         // spans 128 accumulator rows, the rest read stale shared memory and produce rows the epilogue never stores
         CA.init(g.a, g.P, g.R, g.nkb, g.ac_last, pg, GT, ALAY == TCG_LAY_KM ? BM : g.a_atoms * 32);
@@ -742,11 +742,16 @@ inline int encode_f32(CUtensorMap* m, const void* base, int cols, int rows, int 
 
 template <int ALAY, int BLAY, int EPI, int AMODE, int BMODE>
 int launch_cfg(Tcg2Args& a, cudaStream_t st) {
+    // converter groups (several k-blocks in conversion at once) are an opt-in experiment: B200SP_TCG2_GROUPS=2|4.  Measured
+    // (profiles/r2_gemm_variants.txt): +2-4 % on the long-M data-gradient shapes, nothing elsewhere, while the run-time group
+    // geometry costs the single-group path 2.4x more converter instructions -- so the default instantiation has it compiled out.
     using E = ETf;
     static bool attr_set = false;
-    auto kern = tcgemm2_kernel<ALAY, BLAY, EPI, AMODE, BMODE>;
+    auto kern = tcgemm2_kernel<ALAY, BLAY, EPI, AMODE, BMODE, false>;
+    auto kern_g = tcgemm2_kernel<ALAY, BLAY, EPI == TCG_EPI_ATOMIC ? TCG_EPI_ATOMIC : EPI, AMODE, BMODE, EPI != TCG_EPI_ATOMIC>;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+        if (e == cudaSuccess && EPI != TCG_EPI_ATOMIC) e = cudaFuncSetAttribute(kern_g, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
@@ -787,12 +792,8 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st) {
         // converter groups: as many as the rings allow (every ring depth is a multiple of the group count), then deeper rings:
         // raw stages first (they hide the TMA latency and are the cheaper ones), operand stages after
         static int gmax = -1;
-        // measured (profiles/r2_gemm_groups.txt): 2 groups are worth ~4 % on the long-M data-gradient shapes, 4 bring nothing
-        // more (the MMA issue thread becomes the critical path), and the MN-major weight-gradient form is fastest with one
-        if (gmax < 0) { const char* e = getenv("B200SP_TCG2_GROUPS"); gmax = e ? atoi(e) : 2; if (gmax != 1 && gmax != 2 && gmax != 4) gmax = 2; }
-        static int gwg = -1;
-        if (gwg < 0) { const char* e = getenv("B200SP_TCG2_WGRAD_GROUPS"); gwg = e ? atoi(e) : 1; if (gwg != 1 && gwg != 2 && gwg != 4) gwg = 1; }
-        int G = EPI == TCG_EPI_ATOMIC ? gwg : gmax;
+        if (gmax < 0) { const char* e = getenv("B200SP_TCG2_GROUPS"); gmax = e ? atoi(e) : 1; if (gmax != 1 && gmax != 2 && gmax != 4) gmax = 1; }
+        int G = EPI == TCG_EPI_ATOMIC ? 1 : gmax;
         while (G > 1 && !fit(G, G)) G >>= 1;
         if (G == 1) { a.n_op = 2; a.n_raw = 2; } else { a.n_op = G; a.n_raw = G; }
         a.groups = G;
@@ -842,7 +843,7 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st) {
     if (rc) return rc;
     const int total = numPt * numQt * a.splits;
     const int grid = total < NUM_SMS ? total : NUM_SMS;
-    { cudaError_t le = b200sp_launch_pdl(kern, dim3(grid), dim3(NT), smem, st, a); if (le != cudaSuccess) return (int)le; }
+    { cudaError_t le = b200sp_launch_pdl(a.groups > 1 ? kern_g : kern, dim3(grid), dim3(NT), smem, st, a); if (le != cudaSuccess) return (int)le; }
     B200SP_COUNT_LAUNCH();
     B200SP_RETURN_LAST();
 }
