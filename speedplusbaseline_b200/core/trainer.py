@@ -64,12 +64,26 @@ class KRNTrainStep:
             cx = self._fwd_bwd(*self._static)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g1):
-            cx = self._fwd_bwd(*self._static)
-        with torch.cuda.graph(g2):
-            self._update()
-        self._graphs = (g1, g2)
+        import os
+        if self.world > 1 and os.environ.get('B200SP_GRAPH_NCCL', '1') != '0':
+            # ONE graph for the whole step: the NCCL all-reduce of the flat gradient buffer is captured between the backward
+            # kernels and the fused update (NCCL >= 2.9 supports stream capture), so a replay has no host-side gap around the
+            # collective.  An eager all-reduce first: communicator set-up must not happen under capture.
+            self._allreduce()
+            torch.cuda.synchronize()
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                cx = self._fwd_bwd(*self._static)
+                self._allreduce()
+                self._update()
+            self._graphs = (g1, None)
+        else:
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                cx = self._fwd_bwd(*self._static)
+            with torch.cuda.graph(g2):
+                self._update()
+            self._graphs = (g1, g2)
         self._loss3 = cx.loss3
         self._sig = (tuple(images.shape), tuple(target.shape))
 
@@ -87,8 +101,9 @@ class KRNTrainStep:
         self._static[0].copy_(images, non_blocking=True)
         self._static[1].copy_(target, non_blocking=True)
         self._graphs[0].replay()
-        self._allreduce()
-        self._graphs[1].replay()
+        if self._graphs[1] is not None:
+            self._allreduce()
+            self._graphs[1].replay()
         return self._loss3
 
 
