@@ -65,7 +65,9 @@ class KRNTrainStep:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         import os
-        if self.world > 1 and os.environ.get('B200SP_GRAPH_NCCL', '1') != '0':
+        if self.world > 1 and os.environ.get('B200SP_GRAPH_NCCL', '0') == '1':
+            # opt-in (B200SP_GRAPH_NCCL=1).  Measured at N=2 (profiles/r2_ddp_n2.txt): no gain over the eager all-reduce between two
+            # graphs (6.31 vs 6.29 ms) and the process hangs in destroy_process_group afterwards, so it is NOT the default.
             # ONE graph for the whole step: the NCCL all-reduce of the flat gradient buffer is captured between the backward
             # kernels and the fused update (NCCL >= 2.9 supports stream capture), so a replay has no host-side gap around the
             # collective.  An eager all-reduce first: communicator set-up must not happen under capture.

@@ -26,7 +26,7 @@
 #include "tma.cuh"
 
 #ifdef TCG_TIMELINE          // debug build (B200SP_LIB_SUFFIX=_tl B200SP_NVCC_EXTRA=-DTCG_TIMELINE): clock64 stamps of CTA 0, tools/tcg2_timeline.py
-__device__ long long g_tcg2_tl[11][512];
+__device__ long long g_tcg2_tl[14][512];
 #define TL(row, idx) do { if (blockIdx.x == 0 && (idx) < 512) g_tcg2_tl[row][idx] = clock64(); } while (0)
 #else
 #define TL(row, idx) do {} while (0)
@@ -405,9 +405,12 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
             const uint32_t rbase = raw0 + rs * g.raw_stage_bytes;
             const uint32_t a_hi = s_base + os * g.op_stage_bytes, a_lo = a_hi + g.a_op_bytes;
             const uint32_t b_hi = a_hi + b_in_stage, b_lo = b_hi + g.b_op_bytes;
+            if (pt == 0) TL(11, tlc);                           // after the named barrier + phase re-check
             CA.convert(cons.kb, cons.w.p0, rbase, rbase + slotA2 * 8192, a_hi, a_lo);
             if (!g.b_res) CB.convert(cons.kb, cons.w.q0, rbase + slotB * 8192, 0, b_hi, b_lo);
+            if (pt == 0) TL(12, tlc);                           // conversions issued
             tc::fence_proxy_async_smem();
+            if (pt == 0) TL(13, tlc);                           // proxy fence done
             __syncwarp();
             if (lane == 0) { tc::mbar_arrive(&full[os]); tc::mbar_arrive(&rawempty[rs]); }
             if (pt == 0) TL(5, tlc);
@@ -852,7 +855,7 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st) {
 
 #ifdef TCG_TIMELINE
 extern "C" int b200sp_tcg2_timeline(long long* host_out) {
-    return (int)cudaMemcpyFromSymbol(host_out, g_tcg2_tl, sizeof(long long) * 11 * 512);
+    return (int)cudaMemcpyFromSymbol(host_out, g_tcg2_tl, sizeof(long long) * 14 * 512);
 }
 #endif
 

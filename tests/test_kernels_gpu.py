@@ -21,7 +21,9 @@ def _g(seed):
 @pytest.mark.parametrize('M,N,K', [(301, 16, 32), (1000, 96, 16), (257, 24, 144), (2352, 320, 960), (64, 1024, 320), (5, 64, 96),
                                    (40003, 96, 16), (2352, 1024, 1280), (20001, 144, 24), (9408, 576, 96),
                                    # the long-M / tiny-N*K shapes of the direct fp32 kernels (pwdirect.cu), ragged M
-                                   (9409, 16, 32), (12001, 24, 96), (9999, 24, 144), (10001, 32, 144), (9408, 192, 32), (11111, 32, 192)])
+                                   (9409, 16, 32), (12001, 24, 96), (9999, 24, 144), (10001, 32, 144), (9408, 192, 32), (11111, 32, 192),
+                                   # BASELINE.json's full sizes (bs=48, 112x112 maps): M = 602,112
+                                   (602112, 96, 16), (602112, 16, 32)])
 @pytest.mark.parametrize('act', [L.ACT_NONE, L.ACT_RELU6])
 def test_pw_fwd_with_bn_epilogue(M, N, K, act):
     g = _g(M + N + K)
@@ -59,7 +61,8 @@ def test_pw_fwd_bias_act_no_bn():
 
 @pytest.mark.parametrize('M,N,K', [(301, 16, 32), (999, 96, 16), (2352, 1024, 320), (130, 24, 144), (40003, 96, 16), (20001, 24, 144),
                                    (2352, 1024, 1280), (9408, 96, 576), (784, 64, 96),
-                                   (9409, 16, 32), (12001, 24, 96), (20001, 144, 24), (10001, 32, 144), (9408, 192, 32), (11111, 32, 192)])
+                                   (9409, 16, 32), (12001, 24, 96), (20001, 144, 24), (10001, 32, 144), (9408, 192, 32), (11111, 32, 192),
+                                   (602112, 96, 16)])
 @pytest.mark.parametrize('act', [L.ACT_NONE, L.ACT_RELU6, L.ACT_LEAKY02])
 def test_pw_dgrad_fused_bn_backward(M, N, K, act):
     g = _g(M * 3 + N + K + act)
@@ -107,7 +110,7 @@ def test_pw_dgrad_plain_scale():
 
 
 @pytest.mark.parametrize('M,N,K', [(3001, 16, 32), (1999, 96, 16), (2352, 1024, 320), (4097, 24, 144), (100, 64, 96), (60003, 96, 16),
-                                   (2352, 1024, 1280), (9408, 576, 96), (37632, 32, 192), (784, 64, 96), (196, 64, 96)])
+                                   (2352, 1024, 1280), (9408, 576, 96), (37632, 32, 192), (784, 64, 96), (196, 64, 96), (602112, 96, 16)])
 def test_pw_wgrad(M, N, K):
     g = _g(M + 7 * N + K)
     gq, yq = torch.randn(M, N, generator=g), torch.randn(M, N, generator=g)

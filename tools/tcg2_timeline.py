@@ -41,10 +41,10 @@ for _ in range(3):
     flush.zero_()
     run()
 torch.cuda.synchronize()
-buf = (C.c_longlong * (11 * 512))()
+buf = (C.c_longlong * (14 * 512))()
 L.lib.b200sp_tcg2_timeline.argtypes = [C.c_void_p]
 L.lib.b200sp_tcg2_timeline(buf)
-t = [[buf[r * 512 + i] for i in range(512)] for r in range(11)]
+t = [[buf[r * 512 + i] for i in range(512)] for r in range(14)]
 t0 = min(v for v in (t[0][0], t[2][0], t[6][0]) if v > 0)
 print('# %s [%d,%d,%d]  CTA 0, cycles since first stamp' % (op, M, N, K))
 print(' kb | tma: wait   issue | conv: top  rawfull   empty    done  (d_raw d_empty d_conv) | mma: top    full   issued (d_full d_issue) | period')
@@ -71,3 +71,8 @@ for c in range(12):
     nxt = t[10][5 * c + 5]
     print('   chunk %2d: start %8d  ld %5d  corr %5d  stage %5d  store %5d   (next chunk starts +%d)' % (
         c, b[0] - t0, b[1] - b[0], b[2] - b[1], b[3] - b[2], b[4] - b[3], (nxt - b[4]) if nxt else 0))
+print('# converter thread 0, inside a k-block: empty observed -> +barrier/recheck -> +lds/convert/sts issued -> +proxy fence -> +arrive')
+for i in range(min(n, 12)):
+    if t[5][i] == 0:
+        break
+    print('   kb %2d: bar %5d  convert %5d  fence %5d  arrive %5d' % (i, t[11][i] - t[4][i], t[12][i] - t[11][i], t[13][i] - t[12][i], t[5][i] - t[13][i]))
