@@ -54,6 +54,7 @@ struct alignas(64) Tcg2Args {
     int P, Q, R, lda, ldb, ldo;
     int BN, numPt, numQt, splits, kb_per_split, nkb;
     int n_op, n_raw, groups;
+    int stack_b;                     // 3xTF32 with [B hi ; B lo] read by one MMA of width 2*BN (2 issues per k-step instead of 3)
     int nm;                          // operand copies per tile: 2 = (tf32 hi, lo) for 3xTF32, 1 = single-pass TF32 (--use_fp16 mode)
     int b_res;
     int ac_last, nks_last;
@@ -425,6 +426,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
     } else if (warp == MMA_WARP) {
         // ======================================= MMA ISSUER ======================================
         const uint32_t idesc = tc::make_idesc(E::TF32 ? tc::FMT_TF32 : tc::FMT_BF16, ALAY == TCG_LAY_MM, BLAY == TCG_LAY_MM, BM, g.BN);
+        const uint32_t idesc2 = tc::make_idesc(tc::FMT_TF32, ALAY == TCG_LAY_MM, BLAY == TCG_LAY_MM, BM, 2 * g.BN);
         // per-k-step start-address advance (bytes) and LBO / SBO / layout of each operand
         constexpr uint32_t KSTEP_KM = 32, KSTEP_MM = (E::TF32 ? 8 : 16) * 128;
         constexpr uint32_t LBO_MM = E::KE * 128, SBO_MM = E::TF32 ? 512 : 1024;
@@ -466,7 +468,14 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
                     for (int ks = 0; ks < 4; ++ks) {
                         if (ks < nks) {
                             const uint32_t accum = ks > 0 ? 1u : first;
-                            if (g.nm == 2) {
+                            if (g.stack_b) {
+                                // [B hi ; B lo] are adjacent tiles: ONE MMA of width 2*BN computes A_hi*B_hi into the main accumulator
+                                // columns and A_hi*B_lo into the correction columns right behind them; a second one adds A_lo*B_hi
+                                // to the correction columns -- 2 issues per k-step instead of 3 for the same tensor work (the issuing
+                                // thread, ~55 cycles per UTCHMMA, is on the critical path of every k-block: DESIGN.md 3.10)
+                                tc::umma<true>(d_tmem, mk(ah + ks * A_STEP, A_HIW), mk(bh + ks * B_STEP, B_HIW), idesc2, accum);
+                                tc::umma<true>(d_corr, mk(al + ks * A_STEP, A_HIW), mk(bh + ks * B_STEP, B_HIW), idesc, 1u);
+                            } else if (g.nm == 2) {
                                 const bool split = g.acc_cols > g.BN;
                                 tc::umma<true>(d_corr, mk(al + ks * A_STEP, A_HIW), mk(bh + ks * B_STEP, B_HIW), idesc, accum);
                                 tc::umma<true>(d_corr, mk(ah + ks * A_STEP, A_HIW), mk(bl + ks * B_STEP, B_HIW), idesc, 1u);
@@ -826,6 +835,12 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st) {
     const uint32_t smem = a.off_bar + 512 + 1024;
     a.acc_cols = (a.nm == 2 && 2 * 2 * BN <= 512) ? 2 * BN : BN;
     a.nacc = 4 * a.acc_cols <= 512 ? 4 : 2;
+    {
+        static int sb = -1;
+        if (sb < 0) { const char* e = getenv("B200SP_TCG2_STACKB"); sb = (e && e[0] == '0') ? 0 : 1; }
+        // MN-major B: the hi tile must end on an atom boundary for the lo tile to continue the N index
+        a.stack_b = (sb && a.nm == 2 && a.acc_cols == 2 * BN && 2 * BN <= 256 && (BLAY == TCG_LAY_KM || BN % 32 == 0)) ? 1 : 0;
+    }
     a.split_epi = (BN <= 32 && numQt == 1 && EPI_SETS == 2) ? 1 : 0;
     uint32_t cols = 32;
     while (cols < (uint32_t)(a.nacc * a.acc_cols)) cols <<= 1;
