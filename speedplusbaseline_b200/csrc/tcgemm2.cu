@@ -54,6 +54,8 @@ struct alignas(64) Tcg2Args {
     int P, Q, R, lda, ldb, ldo;
     int BN, numPt, numQt, splits, kb_per_split, nkb;
     int n_op, n_raw, groups;
+    int ts;                          // A operand converted into TMEM and consumed by the TS form of tcgen05.mma (K-major A only)
+    uint32_t a_tm_col;               // first TMEM column of the A ring (n_op slots of 64 columns: 32 hi + 32 lo)
     int stack_b;                     // 3xTF32 with [B hi ; B lo] read by one MMA of width 2*BN (2 issues per k-step instead of 3)
     int nm;                          // operand copies per tile: 2 = (tf32 hi, lo) for 3xTF32, 1 = single-pass TF32 (--use_fp16 mode)
     int b_res;
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
     pdl_trigger();
     pdl_wait();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);      // broadcast form: keeps the TMEM address (and everything derived from it) in UNIFORM registers, so tcgen05.mma needs no per-instruction R2UR waterfall
-    const uint32_t b_in_stage = g.nm * g.a_op_bytes;
+    const uint32_t b_in_stage = g.ts ? 0u : g.nm * g.a_op_bytes;
     constexpr int slotA2 = APT, slotB = AMODE == XM_DY ? 2 * APT : APT;     // 8192-byte sub-slots of a raw stage: A | [A2] | B
 
     if (warp == TMA_WARP) {
@@ -407,7 +409,40 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
             const uint32_t a_hi = s_base + os * g.op_stage_bytes, a_lo = a_hi + g.a_op_bytes;
             const uint32_t b_hi = a_hi + b_in_stage, b_lo = b_hi + g.b_op_bytes;
             if (pt == 0) TL(11, tlc);                           // after the named barrier + phase re-check
-            CA.convert(cons.kb, cons.w.p0, rbase, rbase + slotA2 * 8192, a_hi, a_lo);
+            if (ALAY == TCG_LAY_KM && g.ts) {
+                // A straight into tensor memory: warp -> (TMEM lane quarter = CTA warp index & 3, 8-column slice), lane = row.
+                // The raw tile was written by TMA with the 128-byte swizzle, so 8 consecutive rows read 8 different banks groups.
+                const int q = warp & 3, kq = (warp - (TMA_WARP + 1)) >> 2;
+                const int kcol = cons.kb * 32 + kq * 8;
+                if (kcol < g.R) {
+                    const int r = q * 32 + lane;
+                    const uint32_t rowb = s_base + g.off_raw + rs * g.raw_stage_bytes + r * 128;
+                    XfP p0, p1;
+                    const int ch = min(kcol, g.R - 8);
+                    xf_load<AMODE>(g.a, ch, p0);
+                    xf_load<AMODE>(g.a, ch + 4, p1);
+                    const ActP act = act_params(g.a.act);
+                    const uint32_t o0 = (uint32_t)(((kq * 2) ^ (r & 7)) << 4), o1 = (uint32_t)(((kq * 2 + 1) ^ (r & 7)) << 4);
+                    float4 x0 = lds4(rowb + o0), x1 = lds4(rowb + o1), y0 = f4zero(), y1 = f4zero();
+                    if (AMODE == XM_DY) { y0 = lds4(rowb + slotA2 * 8192 + o0); y1 = lds4(rowb + slotA2 * 8192 + o1); }
+                    const float4 v0 = xf_apply<AMODE>(x0, y0, p0, act), v1 = xf_apply<AMODE>(x1, y1, p1, act);
+                    const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                    uint32_t h[8], l[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float hi, lo;
+                        split1(vv[i], hi, lo);
+                        h[i] = __float_as_uint(hi); l[i] = __float_as_uint(lo);
+                    }
+                    const uint32_t ta = tmem_base + g.a_tm_col + os * 64 + kq * 8 + ((uint32_t)(q * 32) << 16);
+                    tc::tmem_st8(ta, h);
+                    if (g.nm == 2) tc::tmem_st8(ta + 32, l);
+                }
+                tc::tmem_st_wait();
+                tc::tc_fence_before();
+            } else {
+                CA.convert(cons.kb, cons.w.p0, rbase, rbase + slotA2 * 8192, a_hi, a_lo);
+            }
             if (!g.b_res) CB.convert(cons.kb, cons.w.q0, rbase + slotB * 8192, 0, b_hi, b_lo);
             if (pt == 0) TL(12, tlc);                           // conversions issued
             tc::fence_proxy_async_smem();
@@ -468,7 +503,19 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
                     for (int ks = 0; ks < 4; ++ks) {
                         if (ks < nks) {
                             const uint32_t accum = ks > 0 ? 1u : first;
-                            if (g.stack_b) {
+                            if (ALAY == TCG_LAY_KM && g.ts) {
+                                const uint32_t at = tmem_base + g.a_tm_col + os * 64 + ks * 8;
+                                if (g.stack_b) {
+                                    tc::umma_ts_tf32(d_tmem, at, mk(bh + ks * B_STEP, B_HIW), idesc2, accum);
+                                    tc::umma_ts_tf32(d_corr, at + 32, mk(bh + ks * B_STEP, B_HIW), idesc, 1u);
+                                } else if (g.nm == 2) {
+                                    tc::umma_ts_tf32(d_corr, at + 32, mk(bh + ks * B_STEP, B_HIW), idesc, accum);
+                                    tc::umma_ts_tf32(d_corr, at, mk(bl + ks * B_STEP, B_HIW), idesc, 1u);
+                                    tc::umma_ts_tf32(d_tmem, at, mk(bh + ks * B_STEP, B_HIW), idesc, accum);
+                                } else {
+                                    tc::umma_ts_tf32(d_tmem, at, mk(bh + ks * B_STEP, B_HIW), idesc, accum);
+                                }
+                            } else if (g.stack_b) {
                                 // [B hi ; B lo] are adjacent tiles: ONE MMA of width 2*BN computes A_hi*B_hi into the main accumulator
                                 // columns and A_hi*B_lo into the correction columns right behind them; a second one adds A_lo*B_hi
                                 // to the correction columns -- 2 issues per k-step instead of 3 for the same tensor work (the issuing
@@ -739,7 +786,7 @@ constexpr uint32_t SMEM_LIMIT = 227 * 1024;
 constexpr uint32_t BRES_LIMIT = 64 * 1024;
 
 // raw fp32 operand stored [rows][ld] with `cols` valid columns: box {32 floats, box_rows}, no swizzle, zero fill
-inline int encode_f32(CUtensorMap* m, const void* base, int cols, int rows, int ld, int box_rows) {
+inline int encode_f32(CUtensorMap* m, const void* base, int cols, int rows, int ld, int box_rows, bool swz128 = false) {
     tma::EncodeTiledFn fn = tma::encode_fn();
     if (!fn) return B200SP_ENOSYS;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -747,7 +794,7 @@ inline int encode_f32(CUtensorMap* m, const void* base, int cols, int rows, int 
     cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
     cuuint32_t es[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : B200SP_ENOSYS;
 }
@@ -775,6 +822,11 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st) {
         a.nks_last = ceil_div(rem, 2 * E::EPV);
         a.ac_last = 2 * a.nks_last;
     }
+    {
+        static int ts_env = -1;
+        if (ts_env < 0) { const char* e = getenv("B200SP_TCG2_TS"); ts_env = (e && e[0] == '1') ? 1 : 0; }
+        a.ts = (ts_env && ALAY == TCG_LAY_KM && a.R >= 8 && a.R % 8 == 0) ? 1 : 0;
+    }
     // ---- tile width: the widest that fits shared memory; narrower while the grid does not cover the machine ----
     bool fits = false;
     for (int cap = 128; cap >= 32 && !fits; cap -= (cap > 64 ? 32 : 16)) {
@@ -794,7 +846,7 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st) {
         const int nb_slots = ceil_div((int)a.b_op_bytes, 8192);
         const uint32_t bres_bytes = (uint32_t)a.nkb * a.nm * a.b_op_bytes;
         a.b_res = (EPI != TCG_EPI_ATOMIC && numQt == 1 && BMODE == XM_PLAIN && bres_bytes <= BRES_LIMIT) ? 1 : 0;
-        a.op_stage_bytes = a.nm * (a.a_op_bytes + (a.b_res ? 0 : a.b_op_bytes));
+        a.op_stage_bytes = a.nm * ((a.ts ? 0 : a.a_op_bytes) + (a.b_res ? 0 : a.b_op_bytes));
         a.raw_stage_bytes = (APT + (AMODE == XM_DY ? APT : 0) + (a.b_res ? 0 : nb_slots)) * 8192;
         if (a.b_res && a.raw_stage_bytes < (uint32_t)nb_slots * 8192) a.raw_stage_bytes = nb_slots * 8192;
         const uint32_t fixed = EPI_W * 32 * STG_LD * 4 + EPI_W * 2 * BN * 4 + 512 + (a.b_res ? bres_bytes : 0);
@@ -805,7 +857,7 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st) {
         // raw stages first (they hide the TMA latency and are the cheaper ones), operand stages after
         static int gmax = -1;
         if (gmax < 0) { const char* e = getenv("B200SP_TCG2_GROUPS"); gmax = e ? atoi(e) : 1; if (gmax != 1 && gmax != 2 && gmax != 4) gmax = 1; }
-        int G = EPI == TCG_EPI_ATOMIC ? 1 : gmax;
+        int G = (EPI == TCG_EPI_ATOMIC || a.ts) ? 1 : gmax;        // the TMEM A path deals one k-block to all 16 converter warps
         while (G > 1 && !fit(G, G)) G >>= 1;
         if (G == 1) { a.n_op = 2; a.n_raw = 2; } else { a.n_op = G; a.n_raw = G; }
         a.groups = G;
@@ -835,6 +887,12 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st) {
     const uint32_t smem = a.off_bar + 512 + 1024;
     a.acc_cols = (a.nm == 2 && 2 * 2 * BN <= 512) ? 2 * BN : BN;
     a.nacc = 4 * a.acc_cols <= 512 ? 4 : 2;
+    if (a.ts) {                      // tensor memory holds the A ring too: n_op slots of 64 columns behind the accumulators
+        int nacc = (512 - a.n_op * 64) / a.acc_cols;
+        if (nacc < 1) return B200SP_ENOSYS;
+        a.nacc = nacc > 4 ? 4 : nacc;
+        a.a_tm_col = (uint32_t)(a.nacc * a.acc_cols);
+    }
     {
         static int sb = -1;
         if (sb < 0) { const char* e = getenv("B200SP_TCG2_STACKB"); sb = (e && e[0] == '0') ? 0 : 1; }
@@ -844,14 +902,14 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st) {
     a.split_epi = (BN <= 32 && numQt == 1 && EPI_SETS == 2) ? 1 : 0;
     uint32_t cols = 32;
     while (cols < (uint32_t)(a.nacc * a.acc_cols)) cols <<= 1;
-    a.tmem_cols = cols;
+    a.tmem_cols = a.ts ? 512u : cols;
     // ---- tensor maps of the raw operands ----
     int rc;
-    if (ALAY == TCG_LAY_KM) { rc = encode_f32(&a.mapA, a.a.x, a.R, a.P, a.lda, BM); a.a_tx = BM * 128; }
+    if (ALAY == TCG_LAY_KM) { rc = encode_f32(&a.mapA, a.a.x, a.R, a.P, a.lda, BM, a.ts != 0); a.a_tx = BM * 128; }
     else                    { rc = encode_f32(&a.mapA, a.a.x, a.P, a.R, a.lda, 32); a.a_tx = a.a_atoms * 4096; }
     if (rc) return rc;
     if (AMODE == XM_DY) {
-        rc = ALAY == TCG_LAY_KM ? encode_f32(&a.mapA2, a.a.x2, a.R, a.P, a.lda, BM) : encode_f32(&a.mapA2, a.a.x2, a.P, a.R, a.lda, 32);
+        rc = ALAY == TCG_LAY_KM ? encode_f32(&a.mapA2, a.a.x2, a.R, a.P, a.lda, BM, a.ts != 0) : encode_f32(&a.mapA2, a.a.x2, a.P, a.R, a.lda, 32);
         if (rc) return rc;
     } else {
         a.mapA2 = a.mapA;
