@@ -38,7 +38,9 @@ def _peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  Sampled in-process through NVML
+    (nvidia_ml_py) every 0.2 s -- spawning `nvidia-smi` five times a second takes the driver lock for tens of milliseconds
+    per call, which showed up as sporadic 20 % dips of the host-driven end-to-end number; `nvidia-smi` is the fallback."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
@@ -46,15 +48,46 @@ class ClockSampler(threading.Thread):
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index, self.rows, self._halt = index, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(vis.split(',')[index]) if vis and vis.split(',')[index].strip().isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.source = 'nvml'
+        except Exception:
+            self.source = 'nvidia-smi'
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+        try:
+            pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+        except Exception:
+            pw = 0.0
+        get = getattr(n, 'nvmlDeviceGetCurrentClocksEventReasons', None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        r = int(get(self.h))
+        bit = lambda name, alt: getattr(n, name, getattr(n, alt, 0))
+        flags = [('Active' if r & bit('nvmlClocksEventReasonHwSlowdown', 'nvmlClocksThrottleReasonHwSlowdown') else 'Not Active'),
+                 ('Active' if r & bit('nvmlClocksEventReasonHwThermalSlowdown', 'nvmlClocksThrottleReasonHwThermalSlowdown') else 'Not Active'),
+                 ('Active' if r & bit('nvmlClocksEventReasonSwThermalSlowdown', 'nvmlClocksThrottleReasonSwThermalSlowdown') else 'Not Active'),
+                 ('Active' if r & bit('nvmlClocksEventReasonSwPowerCap', 'nvmlClocksThrottleReasonSwPowerCap') else 'Not Active')]
+        return [str(sm), str(mx), '%.1f' % pw] + flags
 
     def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(',')]
-                if len(f) >= 7:
-                    self.rows.append(f)
+                if self.nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                    f = [x.strip() for x in out.strip().split(',')]
+                    if len(f) >= 7:
+                        self.rows.append(f)
             except Exception:
                 pass
             self._halt.wait(0.2)
@@ -70,7 +103,7 @@ class ClockSampler(threading.Thread):
                 if v.lower().startswith('active'):
                     reasons.add(name)
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(self.rows)}
+                'reasons': sorted(reasons), 'samples': len(self.rows), 'source': self.source}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -403,8 +403,11 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
                 mbar_wait_guard(&empty[os], opar);
                 if (pt == 0) TL(4, tlc);
             }
-            named_bar(2 + gi, GT);
+            if (GRP) named_bar(2 + gi, GT);
+            else asm volatile("bar.sync 2, %0;" ::"n"(PROD_T) : "memory");      // immediate operands: no register-operand barrier on the default path
+#ifndef TCG2_NO_RECHECK
             tc::mbar_try_wait(&rawfull[rs], rpar);              // completes at once: every thread observes the TMA phase itself
+#endif
             const uint32_t rbase = raw0 + rs * g.raw_stage_bytes;
             const uint32_t a_hi = s_base + os * g.op_stage_bytes, a_lo = a_hi + g.a_op_bytes;
             const uint32_t b_hi = a_hi + b_in_stage, b_lo = b_hi + g.b_op_bytes;
