@@ -716,11 +716,15 @@ int roll_geom(RGeom& gm, dim3& grid, int B, int H, int W, int C, int stride, int
     for (int d = 1; d <= MAXCB && d <= C4; ++d) if (C4 % d == 0) cb = d;
     gm.CB = cb; gm.SPC = RNT / cb;
     gm.nWG = ncolgroups;
-    // split the rolled dimension until ~12 warps/SM x 2 waves of threads exist (segments of >= 8 rows: halo overhead <= 25%)
+    // split the rolled dimension until ~12 warps/SM x 2 waves of threads exist (segments of >= 8 rows: halo overhead <= 25 %).
+    // Finer segments for the small maps (B200SP_DW_SMALLSEG=1: >= 3 rows, 3-4x more CTAs) were measured and are SLOWER
+    // (dw_bwd 1214 -> 1323 us per step, job r2v): those launches are bound by their per-CTA reductions, not by parallelism.
     const long long base = (long long)B * ncolgroups * C4;
     const long long target = (long long)NUM_SMS * 3072;
     int nseg = (int)((target + base - 1) / base);
-    const int maxseg = rows >= 16 ? rows / 8 : 1;
+    static int small_seg = -1;
+    if (small_seg < 0) { const char* e = getenv("B200SP_DW_SMALLSEG"); small_seg = (e && e[0] == '1') ? 1 : 0; }
+    const int maxseg = rows >= 32 ? rows / 8 : (small_seg ? (rows >= 3 ? rows / 3 : 1) : (rows >= 16 ? rows / 8 : 1));
     if (nseg > maxseg) nseg = maxseg;
     if (nseg < 1) nseg = 1;
     gm.SEG = (rows + nseg - 1) / nseg;
