@@ -23,6 +23,7 @@
 #ifndef B200SP_H
 #define B200SP_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -106,6 +107,14 @@ typedef struct b200sp_bnbwd {
 int b200sp_version(void);
 /* number of kernel launches issued through this library since load (the bench's gpu_launches) */
 int64_t b200sp_launch_count(void);
+
+/* Scratch for the presplit GEMM route (tcgemm2.cu PRE mode + opsplit.cu): the 1x1 convolutions whose activation operand has at
+ * most 4096 rows (the 7x7 layers of the KRN at batch 48) write their operands once as tf32 hi/lo planes into this buffer and run a
+ * converter-free TMA -> tcgen05 kernel on them.  `base`: device memory, 256-byte aligned, owned by the caller and alive until
+ * replaced (NULL withdraws it); 96 MB covers every layer of the KRN.  Without a workspace the general kernel is used.  The
+ * first half is reused by every eligible forward / data-gradient call, the second half by every eligible weight-gradient
+ * call: issue each kind on ONE stream at a time (the engines run the weight gradients on a side stream). */
+int b200sp_set_workspace(void *base, size_t bytes);
 
 /* tcgen05 plumbing self-test (tc_probe.cu): D[128,N] = A * B^T on one CTA with operands staged in the
  * library's swizzled shared-memory formats.  mode 0 tf32, 1 3xTF32, 2 bf16; *_major 0: operand given

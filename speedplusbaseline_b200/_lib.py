@@ -83,6 +83,7 @@ PVT, PBF, PBB = C.POINTER(VTensor), C.POINTER(BnFwd), C.POINTER(BnBwd)
 _SIGS = {
     'b200sp_version': ([], i32),
     'b200sp_launch_count': ([], i64),
+    'b200sp_set_workspace': ([vp, C.c_size_t], i32),
     'b200sp_tc_probe': ([vp, vp, vp, i32, i32, i32, i32, i32, i32, vp], i32),
     'b200sp_mma_probe': ([i32, i32, i32, i32, i32, i32, i32, vp, vp], i32),
     'b200sp_stem_fwd': ([vp, vp, vp, PBF, i32, i32, i32, i32, vp], i32),
@@ -163,6 +164,20 @@ def call(name, *args):
 
 def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
+
+
+_workspaces = {}
+
+
+def ensure_workspace(device, nbytes=96 << 20):
+    """Process-lifetime scratch of the presplit GEMM route (include/b200sp.h b200sp_set_workspace), one per device, never freed:
+    the library keeps the raw pointer."""
+    key = torch.device(device).index or 0
+    if key not in _workspaces:
+        _workspaces[key] = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    ws = _workspaces[key]
+    call('b200sp_set_workspace', ws.data_ptr(), ws.numel())
+    return ws
 
 
 def ptr(t):

@@ -507,7 +507,13 @@ extern "C" int b200sp_gemm_wgrad(const b200sp_vtensor* dy, int lddy, const b200s
 // With a single 128-row M tile the K loop (K/8 x 3 tcgen05.mma, ~115 cycles each) is the whole critical path of a CTA;
 // splitting it across CTAs and reducing with fp32 red.add turns 267 us into ~50 us for fc6.  The output must be
 // zero (fwd) or hold the value to accumulate onto (dgrad: the other branch's gradient) on entry.
+int fc_fwd_stream(const float* x, const float* w, float* y_acc, int M, int N, int K, cudaStream_t st);         // fcstream.cu
+int fc_dgrad_stream(const float* dy, const float* w, float* dx_acc, int M, int N, int K, cudaStream_t st);     // fcstream.cu
 extern "C" int b200sp_fc_fwd_splitk(const float* x, const float* w, float* y_acc, int M, int N, int K, void* stream) {
+    {   // batches up to 32 rows: the layer is a pure weight stream (fcstream.cu); larger ones take the split-K tensor-core GEMM
+        const int rc = fc_fwd_stream(x, w, y_acc, M, N, K, (cudaStream_t)stream);
+        if (rc != B200SP_ENOSYS) return rc;
+    }
     TcgProblem p = {};
     p.a = plain_vt(x); p.b = plain_vt(w); p.a_lay = TCG_LAY_KM; p.b_lay = TCG_LAY_KM;
     p.P = M; p.Q = N; p.R = K; p.lda = K; p.ldb = K; p.epi = TCG_EPI_ATOMIC; p.dtype = B200SP_F32;
@@ -515,6 +521,10 @@ extern "C" int b200sp_fc_fwd_splitk(const float* x, const float* w, float* y_acc
     return tcgemm_launch(p, (cudaStream_t)stream);
 }
 extern "C" int b200sp_fc_dgrad_splitk(const float* dy, const float* w, float* dx_acc, int M, int N, int K, void* stream) {
+    {
+        const int rc = fc_dgrad_stream(dy, w, dx_acc, M, N, K, (cudaStream_t)stream);
+        if (rc != B200SP_ENOSYS) return rc;
+    }
     TcgProblem p = {};
     p.a = plain_vt(dy); p.b = plain_vt(w); p.a_lay = TCG_LAY_KM; p.b_lay = TCG_LAY_MM;
     p.P = M; p.Q = K; p.R = N; p.lda = N; p.ldb = K; p.epi = TCG_EPI_ATOMIC; p.dtype = B200SP_F32;

@@ -34,3 +34,20 @@ int tcgemm_launch(const TcgProblem& p, cudaStream_t st);
 
 // second-generation kernel (tcgemm2.cu): raw operands staged by TMA, lean smem->smem converters; same contract.
 int tcgemm2_launch(const TcgProblem& p, cudaStream_t st);
+
+// ---- presplit path (tcgemm2.cu PRE mode + opsplit.cu) ------------------------------------------------------------------------
+// One operand of a GEMM: the virtual tensor stored [rows][ld] with `cols` channels (the per-channel transform indexes the column),
+// written as nm planes (tf32 hi [, lo]) of out[.][out_ld], either in the same orientation or transposed ([cols][rows]).
+struct OpSplitJob {
+    b200sp_vtensor t;
+    int rows, cols, ld;
+    float* out;
+    int out_ld;
+    size_t plane;              // floats between the hi and the lo plane
+    int trans, nm;
+};
+int opsplit_launch(const OpSplitJob& a, const OpSplitJob& b, cudaStream_t st);
+// library-owned scratch for the presplit operands (b200sp_set_workspace); {nullptr, 0} until the host provides one
+void tcg_workspace(float** base, size_t* bytes);
+// 0 | B200SP_ENOSYS (shape not worth it / no workspace: the caller continues with tcgemm2_launch) | cudaError_t
+int tcgemm2_presplit(const TcgProblem& p, cudaStream_t st);

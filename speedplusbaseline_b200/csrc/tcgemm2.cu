@@ -265,7 +265,9 @@ __device__ __forceinline__ void tma_operand(uint32_t dst, const CUtensorMap* m, 
 }
 
 // =====================================================================================================
-template <int ALAY, int BLAY, int EPI, int AMODE, int BMODE, bool GRP>
+// PRE: the operands arrive pre-split (opsplit.cu): K-major planes [hi | lo] that the TMA unit loads straight into the swizzled
+// operand ring -- no raw ring, no converter warps (the kernel is launched with the first PRE_NT threads only).
+template <int ALAY, int BLAY, int EPI, int AMODE, int BMODE, bool GRP, bool PRE = false>
 __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ Tcg2Args g) {
     using T = float;
     using E = ETf;
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
 
     if (tid == 0) {
         const int gw = PROD_T / 32 / (GRP ? g.groups : 1);     // warps per converter group
-        for (int i = 0; i < MAX_OP; ++i) { tc::mbar_init(&full[i], gw); tc::mbar_init(&empty[i], 1); }
+        for (int i = 0; i < MAX_OP; ++i) { tc::mbar_init(&full[i], PRE ? 1 : gw); tc::mbar_init(&empty[i], 1); }
         for (int i = 0; i < 4; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], g.split_epi ? EPI_W / EPI_SETS : EPI_W); }
         tc::mbar_init(bfull, PROD_T / 32);
         for (int i = 0; i < MAX_RAW; ++i) { tc::mbar_init(&rawfull[i], 1); tc::mbar_init(&rawempty[i], gw); }
@@ -314,7 +316,28 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
     const uint32_t b_in_stage = g.ts ? 0u : g.nm * g.a_op_bytes;
     constexpr int slotA2 = APT, slotB = AMODE == XM_DY ? 2 * APT : APT;     // 8192-byte sub-slots of a raw stage: A | [A2] | B
 
-    if (warp == TMA_WARP) {
+    if (PRE && warp == TMA_WARP) {
+        // ======================================= TMA PRODUCER, presplit operands ==================
+        // one 3-d box per operand and k-block: {32 floats, tile rows, planes} lands as the hi tile followed by the lo tile,
+        // 128-byte rows with the hardware swizzle = the K-major UMMA layout; rows / columns out of range are zero-filled
+        if (tc::elect_one()) {
+            int os = 0;
+            uint32_t opar = 1;
+            const uint32_t tx = (uint32_t)g.nm * (g.a_tx + g.b_tx);
+            KIter f;
+            f.init(g, blockIdx.x, total, gridDim.x);
+            while (f.valid()) {
+                mbar_wait_guard(&empty[os], opar);
+                const uint32_t a_hi = s_base + os * g.op_stage_bytes;
+                const uint32_t bar = tc::smem_u32(&full[os]);
+                tc::mbar_arrive_expect_tx(&full[os], tx);
+                tma::load_3d(a_hi, &g.mapA, bar, f.kb * 32, f.w.p0, 0);
+                tma::load_3d(a_hi + b_in_stage, &g.mapB, bar, f.kb * 32, f.w.q0, 0);
+                if (++os == g.n_op) { os = 0; opar ^= 1; }
+                f.next(g);
+            }
+        }
+    } else if (warp == TMA_WARP) {
         // ======================================= TMA PRODUCER =====================================
         if (tc::elect_one()) {
             int rs = 0;
@@ -346,7 +369,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
                 f.next(g);
             }
         }
-    } else if (warp > TMA_WARP) {
+    } else if (!PRE && warp > TMA_WARP) {
         // ======================================= CONVERTERS =======================================
         // `groups` converter groups of GT = 512/groups threads; group gi owns the k-block sequence numbers n = gi (mod groups) of
         // this CTA's stream [resident-B k-blocks | (tile, k-block) items] -- several k-blocks are in conversion at once, which is
@@ -559,9 +582,11 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
         T* outT = reinterpret_cast<T*>(g.out);
         float* outF = reinterpret_cast<float*>(g.out);
         const int nchunks = (g.BN + 31) >> 5;
-        int last_chunk = -1;                            // last chunk this warp reads from TMEM
-        const int c_first = g.split_epi ? 0 : half, c_step = g.split_epi ? 1 : EPI_SETS;
-        for (int c = c_first; c < nchunks; c += c_step) last_chunk = c;
+        // The two warp sets (4 TMEM lane quarters each) share a tile by 32-column chunks, chunk ci to set (ci + tile index) & 1:
+        // with an odd chunk count (96- and 80-wide tiles of the long-M layers) a fixed assignment left one set with twice the
+        // work of the other on EVERY tile (r2f timeline: 5.4 k cycles per 128x96 tile, 2 chunks on the critical path); rotated,
+        // each set drains 3 chunks per 2 tiles.  The sets wait for their accumulator independently, so one can run a tile ahead.
+        const int c_step = g.split_epi ? 1 : EPI_SETS;
         int ni = 0;
         int cur_q0 = -1;
         auto flush = [&](int q0) {
@@ -592,6 +617,8 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
             const Item w = get_item(g, it);
             if (do_stats && cur_q0 >= 0 && cur_q0 != w.q0) flush(cur_q0);
             cur_q0 = w.q0;
+            const int c_first = g.split_epi ? 0 : ((half + ni) & (EPI_SETS - 1));
+            const int last_chunk = c_first < nchunks ? c_first + ((nchunks - 1 - c_first) / c_step) * c_step : -1;
             if (EPI == TCG_EPI_DGRAD && (g.has_bnb || g.skip)) {
                 // the saved conv output y (activation mask / BN reductions) and the skip gradient of this tile are pulled into L2
                 // now, while the main loop still runs: the epilogue's loads then cost an L2 hit instead of a DRAM round trip
@@ -612,9 +639,8 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
                 }
             }
             {   // one polling warp per epilogue set, the others wait on a named barrier (ids 6 / 7; 2..5 belong to the converter groups)
-                const int set = g.split_epi ? half : 0;
-                if ((warp & 3) == 0 && (g.split_epi || warp == 0)) mbar_wait_sleep(&tfull[acc], tpar, g.epi_sleep);
-                named_bar(6 + set, g.split_epi ? 128 : EPI_T);
+                if ((warp & 3) == 0) mbar_wait_sleep(&tfull[acc], tpar, g.epi_sleep);
+                named_bar(6 + half, 128);
             }
             if (tid == 0) TL(9, 2 * ni);
             tc::tc_fence_after();
@@ -927,7 +953,172 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st) {
     B200SP_RETURN_LAST();
 }
 
+constexpr int PRE_NT = EPI_T + MMA_T + TMA_T;
+
+// planes [nm][rows][ld] of a presplit operand: {R, rows, nm} with a {32, box_rows, nm} box, 128-byte swizzle, zero fill
+inline int encode_planes(CUtensorMap* m, const float* base, int R, int rows, int ld, size_t plane, int nm, int box_rows) {
+    tma::EncodeTiledFn fn = tma::encode_fn();
+    if (!fn) return B200SP_ENOSYS;
+    cuuint64_t dims[3] = {(cuuint64_t)R, (cuuint64_t)rows, (cuuint64_t)nm};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(nm > 1 ? plane : (size_t)rows * ld) * 4};
+    cuuint32_t box[3] = {32, (cuuint32_t)box_rows, (cuuint32_t)nm};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : B200SP_ENOSYS;
+}
+
+// cycles of one k-block of a 128 x BN tile in PRE mode (MMA issue + tensor pipe, r2 timelines) and of a tile's fixed part
+inline long long pre_cost(int tiles, int kb_per_tile, int BN) {
+    const long long waves = ceil_div(tiles, NUM_SMS);
+    return waves * ((long long)kb_per_tile * (8 * BN + 250) + 40 * BN + 1500);
+}
+
+template <int EPI>
+int launch_pre(Tcg2Args& a, const float* A, int lda, size_t planeA, const float* B, int ldb, size_t planeB, cudaStream_t st) {
+    using E = ETf;
+    auto kern = tcgemm2_kernel<TCG_LAY_KM, TCG_LAY_KM, EPI, XM_PLAIN, XM_PLAIN, false, true>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int numPt = ceil_div(a.P, BM);
+    a.nkb = ceil_div(a.R, E::KE);
+    {
+        const int rem = a.R - (a.nkb - 1) * E::KE;
+        a.nks_last = ceil_div(rem, 2 * E::EPV);
+        a.ac_last = 2 * a.nks_last;
+    }
+    // ---- tile width and (weight gradient) split-K factor: fewest waves x cycles per wave ----
+    int bestBN = 0, bestS = 1;
+    long long best = -1;
+    static int cap_env = -1;
+    if (cap_env < 0) { const char* e = getenv("B200SP_TCG2_PRE_BN"); cap_env = e ? atoi(e) : 0; }      // experiments: force the tile width cap
+    for (int cap = cap_env ? cap_env : 128; cap >= (cap_env ? cap_env : 32); cap -= 16) {
+        const int nq = ceil_div(a.Q, cap);
+        const int BN = ceil_div(ceil_div(a.Q, nq), 16) * 16;
+        if (BN > cap) continue;
+        const int smax = EPI == TCG_EPI_ATOMIC ? (a.nkb / 4 > 0 ? (a.nkb / 4 < 8 ? a.nkb / 4 : 8) : 1) : 1;
+        for (int sp = 1; sp <= smax; ++sp) {
+            const int kps = ceil_div(a.nkb, sp);
+            if (ceil_div(a.nkb, kps) != sp) continue;
+            const long long c = pre_cost(numPt * nq * sp, kps, BN) + (sp > 1 ? 300 : 0);
+            if (best < 0 || c < best) { best = c; bestBN = BN; bestS = sp; }
+        }
+    }
+    const int BN = bestBN, numQt = ceil_div(a.Q, BN);
+    a.BN = BN; a.numPt = numPt; a.numQt = numQt;
+    a.splits = bestS;
+    a.kb_per_split = ceil_div(a.nkb, a.splits);
+    a.a_op_bytes = BM * 128;
+    a.b_op_bytes = BN * 128;
+    a.a_tx = a.a_op_bytes; a.b_tx = a.b_op_bytes;
+    a.b_res = 0; a.ts = 0; a.groups = 1; a.n_raw = 1; a.raw_stage_bytes = 0;
+    a.op_stage_bytes = a.nm * (a.a_op_bytes + a.b_op_bytes);
+    const uint32_t fixed = EPI_W * 32 * STG_LD * 4 + EPI_W * 2 * BN * 4 + 512 + 1088 + 1024;
+    a.n_op = MAX_OP;
+    while (a.n_op > 1 && a.n_op * a.op_stage_bytes + fixed > SMEM_LIMIT) --a.n_op;
+    if (a.n_op < 2) return B200SP_ENOSYS;
+    a.off_bres = a.n_op * a.op_stage_bytes;
+    a.off_raw = a.off_bres;
+    a.off_stg = a.off_raw;
+    a.off_stat = a.off_stg + EPI_W * 32 * STG_LD * 4;
+    a.off_bar = (a.off_stat + EPI_W * 2 * BN * 4 + 15) & ~15u;
+    const uint32_t smem = a.off_bar + 512 + 1024;
+    a.acc_cols = (a.nm == 2 && 2 * 2 * BN <= 512) ? 2 * BN : BN;
+    a.nacc = 4 * a.acc_cols <= 512 ? 4 : 2;
+    a.stack_b = (a.nm == 2 && a.acc_cols == 2 * BN && 2 * BN <= 256) ? 1 : 0;
+    a.split_epi = (BN <= 32 && numQt == 1 && EPI_SETS == 2) ? 1 : 0;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(a.nacc * a.acc_cols)) cols <<= 1;
+    a.tmem_cols = cols;
+    int rc = encode_planes(&a.mapA, A, a.R, a.P, lda, planeA, a.nm, BM);
+    if (rc) return rc;
+    rc = encode_planes(&a.mapB, B, a.R, a.Q, ldb, planeB, a.nm, BN);
+    if (rc) return rc;
+    a.mapA2 = a.mapA;
+    const int total = numPt * numQt * a.splits;
+    const int grid = total < NUM_SMS ? total : NUM_SMS;
+    { cudaError_t le = b200sp_launch_pdl(kern, dim3(grid), dim3(PRE_NT), smem, st, a); if (le != cudaSuccess) return (int)le; }
+    B200SP_COUNT_LAUNCH();
+    B200SP_RETURN_LAST();
+}
+
+float* g_ws_base = nullptr;
+size_t g_ws_bytes = 0;
+
 }  // namespace
+
+extern "C" int b200sp_set_workspace(void* base, size_t bytes) {
+    if (((uintptr_t)base & 255) != 0) return B200SP_EINVAL;
+    g_ws_base = reinterpret_cast<float*>(base);
+    g_ws_bytes = base ? bytes : 0;
+    return 0;
+}
+void tcg_workspace(float** base, size_t* bytes) { *base = g_ws_base; *bytes = g_ws_bytes; }
+
+// Presplit route for the tensor-bound, L2-resident layers: reduction-side rows <= B200SP_TCG2_PRE_M (default 4096: the 7x7 layers
+// at the benchmark batch), both other extents at least 64.  See opsplit.cu for why.
+int tcgemm2_presplit(const TcgProblem& p, cudaStream_t st) {
+    static int on = -1, max_m = 4096;
+    if (on < 0) {
+        const char* e = getenv("B200SP_TCG2_PRE");
+        on = (e && e[0] == '0') ? 0 : 1;
+        const char* m = getenv("B200SP_TCG2_PRE_M");
+        if (m) max_m = atoi(m);
+    }
+    if (!on || !g_ws_base) return B200SP_ENOSYS;
+    if (p.dtype != B200SP_F32 && p.dtype != B200SP_F32_TF32X1) return B200SP_ENOSYS;
+    if (p.b.mode == B200SP_VT_DY) return B200SP_ENOSYS;
+    if ((p.a.mode == B200SP_VT_BNACT && p.a.act == B200SP_ACT_SIGMOID) || (p.b.mode == B200SP_VT_BNACT && p.b.act == B200SP_ACT_SIGMOID)) return B200SP_ENOSYS;
+    // M of the layer: rows of the activation operand (P in fwd / dgrad, the reduction in wgrad)
+    const int m_layer = p.epi == TCG_EPI_ATOMIC ? p.R : p.P;
+    if (m_layer > max_m || m_layer < 256 || p.R < 128 || p.Q < 64 || p.P < 64) return B200SP_ENOSYS;
+    if (p.P % 4 || p.Q % 4 || p.R % 4 || p.lda % 4 || p.ldb % 4) return B200SP_ENOSYS;
+    const int ldo = p.ldo > 0 ? p.ldo : p.Q;
+    if (ldo % 4) return B200SP_ENOSYS;
+    if (((uintptr_t)p.a.x | (uintptr_t)p.b.x | (uintptr_t)p.a.x2 | (uintptr_t)p.out) & 15) return B200SP_ENOSYS;
+    const int nm = p.dtype == B200SP_F32_TF32X1 ? 1 : 2;
+    // planes [nm][P][R] and [nm][Q][R] (R padded to a multiple of 4 floats = the 16-byte stride granularity of a tensor map)
+    const int ldk = (p.R + 3) & ~3;
+    const size_t planeA = ((size_t)p.P * ldk + 63) & ~(size_t)63, planeB = ((size_t)p.Q * ldk + 63) & ~(size_t)63;
+    // the engines run the weight gradients on a second stream, concurrently with the data gradients: each kind has its own half
+    const size_t half = (g_ws_bytes / 2) & ~(size_t)255;
+    if ((nm * (planeA + planeB)) * sizeof(float) > half) return B200SP_ENOSYS;
+    float* wa = g_ws_base + (p.epi == TCG_EPI_ATOMIC ? half / sizeof(float) : 0);
+    float* wb = wa + nm * planeA;
+    OpSplitJob ja, jb;
+    memset(&ja, 0, sizeof(ja)); memset(&jb, 0, sizeof(jb));
+    ja.t = p.a; jb.t = p.b;
+    ja.trans = p.a_lay == TCG_LAY_MM; jb.trans = p.b_lay == TCG_LAY_MM;
+    // stored shapes: K-major [MN][R]; MN-major [R][MN]
+    ja.rows = ja.trans ? p.R : p.P; ja.cols = ja.trans ? p.P : p.R; ja.ld = p.lda;
+    jb.rows = jb.trans ? p.R : p.Q; jb.cols = jb.trans ? p.Q : p.R; jb.ld = p.ldb;
+    ja.out = wa; ja.out_ld = ldk; ja.plane = planeA; ja.nm = nm;
+    jb.out = wb; jb.out_ld = ldk; jb.plane = planeB; jb.nm = nm;
+    int rc = opsplit_launch(ja, jb, st);
+    if (rc) return rc;
+    Tcg2Args a;
+    memset(&a, 0, sizeof(a));
+    a.a = p.a; a.b = p.b;
+    a.a.mode = a.b.mode = B200SP_VT_PLAIN;
+    a.P = p.P; a.Q = p.Q; a.R = p.R; a.lda = ldk; a.ldb = ldk;
+    a.ldo = ldo;
+    a.out = p.out; a.bias = p.bias; a.out_act = p.out_act;
+    a.has_bnf = p.bnf != nullptr;
+    if (p.bnf) a.bnf = *p.bnf;
+    a.skip = p.skip; a.scale_out = p.scale_out;
+    a.has_bnb = p.bnb != nullptr;
+    if (p.bnb) a.bnb = *p.bnb;
+    a.count = p.count;
+    a.epi_sleep = 512;
+    a.nm = nm;
+    if (p.epi == TCG_EPI_FWD) return launch_pre<TCG_EPI_FWD>(a, wa, ldk, planeA, wb, ldk, planeB, st);
+    if (p.epi == TCG_EPI_DGRAD) return launch_pre<TCG_EPI_DGRAD>(a, wa, ldk, planeA, wb, ldk, planeB, st);
+    return launch_pre<TCG_EPI_ATOMIC>(a, wa, ldk, planeA, wb, ldk, planeB, st);
+}
 
 #ifdef TCG_TIMELINE
 extern "C" int b200sp_tcg2_timeline(long long* host_out) {
@@ -937,6 +1128,10 @@ extern "C" int b200sp_tcg2_timeline(long long* host_out) {
 
 int tcgemm2_launch(const TcgProblem& p, cudaStream_t st) {
     if (p.dtype != B200SP_F32 && p.dtype != B200SP_F32_TF32X1) return B200SP_ENOSYS;
+    {   // tensor-bound L2-resident layers: operands split once by a pre-pass, TMA -> MMA with no converters
+        const int rc = tcgemm2_presplit(p, st);
+        if (rc != B200SP_ENOSYS) return rc;
+    }
     if (p.Q % 4 || p.lda % 4 || p.ldb % 4) return B200SP_ENOSYS;
     if (p.a_lay == TCG_LAY_KM ? (p.R % 4) : (p.P % 4)) return B200SP_ENOSYS;
     if (p.b_lay == TCG_LAY_KM ? (p.R % 4) : (p.Q % 4)) return B200SP_ENOSYS;

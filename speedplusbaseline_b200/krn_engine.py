@@ -111,6 +111,7 @@ class KRNEngine:
         self.store = ParamStore(W, BN, self.device)
         self.blocks = _blocks()
         self._ctxs = {}
+        L.ensure_workspace(self.device)       # presplit route of the 7x7-layer GEMMs (tcgemm2.cu PRE mode)
         self.tdtype = torch.float32 if dtype == L.F32 else torch.bfloat16
         import os
         self._async_wgrad = os.environ.get('B200SP_ASYNC_WGRAD', '1') != '0'

@@ -101,7 +101,7 @@ def test_ctypes_signatures_match_header_prototypes():
             if not is_ptr_c:
                 base = p.replace('const', '').split()[0]
                 want = {'int': (C.c_int,), 'int32_t': (C.c_int,), 'float': (C.c_float,), 'double': (C.c_double,),
-                        'int64_t': (C.c_int64,), 'uint64_t': (C.c_uint64,), 'uint32_t': (C.c_uint32,)}[base]
+                        'int64_t': (C.c_int64,), 'uint64_t': (C.c_uint64,), 'uint32_t': (C.c_uint32,), 'size_t': (C.c_size_t, C.c_uint64)}[base]
                 assert t in want, (name, p, t)
 
 

@@ -39,15 +39,46 @@ def timeit(fn, reps):
     return ts[len(ts) // 2]
 
 
+def timeit_graph(fn, reps):
+    """`reps` back-to-back calls captured in ONE CUDA graph (what the train step does): no host launch cost between the kernels,
+    programmatic dependent launch active, operands L2-warm.  Returns us per call."""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3 / reps)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--shapes', nargs='*', default=None)
     ap.add_argument('--reps', type=int, default=10)
     ap.add_argument('--ops', default='fwd,dgrad,wgrad')
+    ap.add_argument('--graph', action='store_true', help='time the calls inside one CUDA graph (no host launch gaps, L2-warm)')
     args = ap.parse_args()
     shapes = KRN if not args.shapes else [tuple(int(v) for v in s.split(',')) for s in args.shapes]
     ops = args.ops.split(',')
     dev = 'cuda'
+    if os.environ.get('B200SP_WS', '1') != '0':       # presplit route of the <= 4096-row layers (B200SP_WS=0: general kernel only)
+        L.ensure_workspace(dev)
     print('%-22s %-6s %9s %9s %9s' % ('shape [M,N,K]', 'op', 'us', 'GB/s', 'TFLOP/s'))
     for M, N, K in shapes:
         x = torch.randn(M, K, device=dev)
@@ -73,7 +104,7 @@ def main():
         }
         for op in ops:
             fn, nbytes = runs[op]
-            us = timeit(fn, args.reps)
+            us = timeit_graph(fn, max(args.reps, 20)) if args.graph else timeit(fn, args.reps)
             print('%-22s %-6s %9.1f %9.1f %9.2f' % ('[%d,%d,%d]' % (M, N, K), op, us, nbytes / us / 1e3, flops / us / 1e6), flush=True)
 
 
