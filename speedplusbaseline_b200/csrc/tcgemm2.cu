@@ -34,14 +34,14 @@ __device__ long long g_tcg2_tl[14][512];
 
 namespace {
 
-constexpr int EPI_T = 256, MMA_T = 32, TMA_T = 32, PROD_T = 512;
-constexpr int APT = 1024 / PROD_T;              // 16-byte pieces of a 128-row x 128-byte tile per converter thread
-constexpr int EPI_W = EPI_T / 32;
-constexpr int EPI_SETS = EPI_W / 4;
-constexpr int MMA_WARP = EPI_W;
-constexpr int TMA_WARP = EPI_W + 1;
-constexpr int PROD_TID0 = EPI_T + MMA_T + TMA_T;
-constexpr int NT = EPI_T + MMA_T + TMA_T + PROD_T;     // 832 threads
+// 832 threads in two role splits (template parameter EW = epilogue warps):
+//   EW =  8:  8 epilogue warps | MMA warp | TMA warp | 16 converter warps   -- main-loop-bound shapes
+//   EW = 16: 16 epilogue warps | MMA warp | TMA warp |  8 converter warps   -- short-K shapes: their epilogue is a chain of dependent
+//            instructions per warp (~12 cycles per instruction, schedulers 17 % busy: r3d ncu capture of dgrad [150528,24,144]),
+//            so it scales with the number of warps draining chunks while the converters sit idle 70 % of the time
+constexpr int MMA_T = 32, TMA_T = 32;
+constexpr int NT = 832;
+constexpr int A_SLOTS = 2;                      // 8192-byte sub-slots of a raw 128-row x 128-byte tile
 constexpr int BM = 128;
 constexpr int STG_LD = 36;
 constexpr int MAX_OP = 4, MAX_RAW = 8;
@@ -81,7 +81,7 @@ struct alignas(64) Tcg2Args {
     uint32_t epi_sleep;
 };
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_T) : "memory"); }
+template <int T> __device__ __forceinline__ void epi_bar_t() { asm volatile("bar.sync 1, %0;" ::"n"(T) : "memory"); }
 // Waiting on an mbarrier costs issue slots: try_wait's suspend window is short and ends on any barrier activity, so a waiting warp
 // re-polls continuously (r2c ncu capture of the long-M forward: 62 % of ALL executed warp-instructions were the 16 converter
 // warps polling `empty`).  Hence ONE warp per role polls and releases the others through a hardware named barrier, on
@@ -104,30 +104,53 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, 
 }
 
 struct Item { int p0, q0, kb0, kb1; };
-__device__ __forceinline__ Item get_item(const Tcg2Args& g, int it) {
-    Item w;
-    const int qt = it % g.numQt;
-    const int t2 = it / g.numQt;
-    const int pt = t2 % g.numPt, sp = t2 / g.numPt;
-    w.p0 = pt * BM;
-    w.q0 = qt * g.BN;
-    w.kb0 = sp * g.kb_per_split;
-    w.kb1 = min(g.nkb, w.kb0 + g.kb_per_split);
-    return w;
-}
+// Tile coordinates of the items it, it + stride, it + 2 stride, ... without divisions: it = (sp * numPt + pt) * numQt + qt is
+// advanced digit by digit.  get_item's four div / mod per tile were 11 % of ALL executed warp-instructions of the long-M kernels
+// (r3d ncu capture) and sit on the dependent-instruction chain of every role.
+struct TileIter {
+    int qt, pt, sp, dq, dp, ds;
+    __device__ __forceinline__ void init(const Tcg2Args& g, int it, int stride) {
+        qt = it % g.numQt;
+        const int t2 = it / g.numQt;
+        pt = t2 % g.numPt; sp = t2 / g.numPt;
+        dq = stride % g.numQt;
+        const int d2 = stride / g.numQt;
+        dp = d2 % g.numPt; ds = d2 / g.numPt;
+    }
+    __device__ __forceinline__ void step(const Tcg2Args& g) {
+        qt += dq;
+        int c = 0;
+        if (qt >= g.numQt) { qt -= g.numQt; c = 1; }
+        pt += dp + c;
+        c = 0;
+        if (pt >= g.numPt) { pt -= g.numPt; c = 1; }
+        sp += ds + c;
+    }
+    __device__ __forceinline__ Item item(const Tcg2Args& g) const {
+        Item w;
+        w.p0 = pt * BM;
+        w.q0 = qt * g.BN;
+        w.kb0 = sp * g.kb_per_split;
+        w.kb1 = min(g.nkb, w.kb0 + g.kb_per_split);
+        return w;
+    }
+};
 struct KIter {
     int it, total, stride;
+    TileIter ti;
     Item w;
     int kb;
     __device__ __forceinline__ void init(const Tcg2Args& g, int first, int total_, int stride_) {
         it = first; total = total_; stride = stride_;
-        if (it < total) { w = get_item(g, it); kb = w.kb0; }
+        ti.init(g, first, stride_);
+        if (it < total) { w = ti.item(g); kb = w.kb0; }
     }
     __device__ __forceinline__ bool valid() const { return it < total; }
     __device__ __forceinline__ void next(const Tcg2Args& g) {
         if (++kb >= w.kb1) {
             it += stride;
-            if (it < total) { w = get_item(g, it); kb = w.kb0; }
+            ti.step(g);
+            if (it < total) { w = ti.item(g); kb = w.kb0; }
         }
     }
 };
@@ -188,8 +211,9 @@ __device__ __forceinline__ void split_store(float4 v, uint32_t dst_hi, uint32_t 
 // The operand tile uses the same (atom, row, chunk) with the UMMA swizzle applied to the chunk index.  A converter GROUP of
 // GT threads (GT = 512 / groups, a multiple of 128) deals the pieces q = pg + i*GT: the chunk index and the swizzle phase of
 // a thread's pieces never change (GT/8 rows is a multiple of 8), so source and destination both advance by GT*16 bytes.
-template <int LAY, int MODE, bool GRP>
+template <int LAY, int MODE, bool GRP, int PROD_T>
 struct Conv {
+    static constexpr int APT = 1024 / PROD_T;       // 16-byte pieces of a 128-row x 128-byte tile per converter thread
     b200sp_vtensor vt;
     ActP act;
     int R, nkb, ac_last, mn_ext;
@@ -267,10 +291,13 @@ __device__ __forceinline__ void tma_operand(uint32_t dst, const CUtensorMap* m, 
 // =====================================================================================================
 // PRE: the operands arrive pre-split (opsplit.cu): K-major planes [hi | lo] that the TMA unit loads straight into the swizzled
 // operand ring -- no raw ring, no converter warps (the kernel is launched with the first PRE_NT threads only).
-template <int ALAY, int BLAY, int EPI, int AMODE, int BMODE, bool GRP, bool PRE = false>
+template <int ALAY, int BLAY, int EPI, int AMODE, int BMODE, bool GRP, bool PRE = false, int EW = 8>
 __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ Tcg2Args g) {
     using T = float;
     using E = ETf;
+    constexpr int EPI_W = EW, EPI_T = EW * 32, EPI_SETS = EW / 4, MMA_WARP = EW, TMA_WARP = EW + 1;
+    constexpr int PROD_TID0 = EPI_T + MMA_T + TMA_T, PROD_T = NT - PROD_TID0;
+    auto epi_bar = [] { epi_bar_t<EPI_T>(); };
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t s_base = tc::smem_u32(smem);
@@ -291,7 +318,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
     if (tid == 0) {
         const int gw = PROD_T / 32 / (GRP ? g.groups : 1);     // warps per converter group
         for (int i = 0; i < MAX_OP; ++i) { tc::mbar_init(&full[i], PRE ? 1 : gw); tc::mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 4; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], g.split_epi ? EPI_W / EPI_SETS : EPI_W); }
+        for (int i = 0; i < 4; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], g.split_epi ? 4 : EPI_W); }
         tc::mbar_init(bfull, PROD_T / 32);
         for (int i = 0; i < MAX_RAW; ++i) { tc::mbar_init(&rawfull[i], 1); tc::mbar_init(&rawempty[i], gw); }
         tc::mbar_fence_init();
@@ -314,7 +341,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
     pdl_wait();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);      // broadcast form: keeps the TMEM address (and everything derived from it) in UNIFORM registers, so tcgen05.mma needs no per-instruction R2UR waterfall
     const uint32_t b_in_stage = g.ts ? 0u : g.nm * g.a_op_bytes;
-    constexpr int slotA2 = APT, slotB = AMODE == XM_DY ? 2 * APT : APT;     // 8192-byte sub-slots of a raw stage: A | [A2] | B
+    constexpr int slotA2 = A_SLOTS, slotB = AMODE == XM_DY ? 2 * A_SLOTS : A_SLOTS;     // 8192-byte sub-slots of a raw stage: A | [A2] | B
 
     if (PRE && warp == TMA_WARP) {
         // ======================================= TMA PRODUCER, presplit operands ==================
@@ -379,8 +406,8 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
         const int G = GRP ? g.groups : 1, GT = GRP ? PROD_T / G : PROD_T;       // GRP == false: one group, everything below folds to constants
         const int gi = pt / GT, pg = pt - gi * GT;
         const bool poller = (pg >> 5) == 0;                      // first warp of the group polls the mbarriers
-        Conv<ALAY, AMODE, GRP> CA;
-        Conv<BLAY, BMODE, GRP> CB;
+        Conv<ALAY, AMODE, GRP, PROD_T> CA;
+        Conv<BLAY, BMODE, GRP, PROD_T> CB;
         // MN-major A (weight gradient): only the atoms that hold columns of the operand are fetched and converted -- the MMA still
         // spans 128 accumulator rows, the rest read stale shared memory and produce rows the epilogue never stores
         CA.init(g.a, g.P, g.R, g.nkb, g.ac_last, pg, GT, ALAY == TCG_LAY_KM ? BM : g.a_atoms * 32);
@@ -503,8 +530,10 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
         if (g.b_res) { mbar_wait_guard(bfull, 0, g.wait_mode); tc::tc_fence_after(); }
         int os = 0, acc = 0, tlm = 0;
         uint32_t fpar = 0, tpar = 1;
-        for (int it = blockIdx.x; it < total; it += gridDim.x) {
-            const Item w = get_item(g, it);
+        TileIter ti;
+        ti.init(g, blockIdx.x, gridDim.x);
+        for (int it = blockIdx.x; it < total; it += gridDim.x, ti.step(g)) {
+            const Item w = ti.item(g);
             mbar_wait_guard(&tempty[acc], tpar, g.wait_mode);
             tc::tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * g.acc_cols;
@@ -570,7 +599,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
         }
     } else {
         // ======================================= EPILOGUE ========================================
-        const int lq = warp & 3, half = warp >> 2;      // TMEM lane quarter, column-chunk parity
+        const int lq = warp & 3, half = warp >> 2;      // TMEM lane quarter, warp set (0 .. EPI_SETS-1)
         float* stg = reinterpret_cast<float*>(smem + g.off_stg) + warp * (32 * STG_LD);
         const uint32_t stg_u = tc::smem_u32(stg);
         float* stat_all = reinterpret_cast<float*>(smem + g.off_stat);      // [EPI_W][2][BN]
@@ -610,15 +639,17 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
         int acc = -1;
         int tle = 0;
         uint32_t tpar = 1;
-        for (int it = blockIdx.x; it < total; it += gridDim.x, ++ni) {
+        TileIter ti;
+        ti.init(g, blockIdx.x, gridDim.x);
+        for (int it = blockIdx.x; it < total; it += gridDim.x, ++ni, ti.step(g)) {
             if (++acc == g.nacc) acc = 0;
             if (acc == 0) tpar ^= 1;
-            if (g.split_epi && (ni & 1) != half) continue;      // the other warp set drains this tile
-            const Item w = get_item(g, it);
+            if (g.split_epi && (ni & (EPI_SETS - 1)) != half) continue;      // another warp set drains this tile
+            const Item w = ti.item(g);
             if (do_stats && cur_q0 >= 0 && cur_q0 != w.q0) flush(cur_q0);
             cur_q0 = w.q0;
             const int c_first = g.split_epi ? 0 : ((half + ni) & (EPI_SETS - 1));
-            const int last_chunk = c_first < nchunks ? c_first + ((nchunks - 1 - c_first) / c_step) * c_step : -1;
+            const int last_chunk = c_first < nchunks ? c_first + ((nchunks - 1 - c_first) & ~(c_step - 1)) : -1;      // c_step is a power of two
             if (EPI == TCG_EPI_DGRAD && (g.has_bnb || g.skip)) {
                 // the saved conv output y (activation mask / BN reductions) and the skip gradient of this tile are pulled into L2
                 // now, while the main loop still runs: the epilogue's loads then cost an L2 hit instead of a DRAM round trip
@@ -828,15 +859,18 @@ inline int encode_f32(CUtensorMap* m, const void* base, int cols, int rows, int 
     return r == CUDA_SUCCESS ? 0 : B200SP_ENOSYS;
 }
 
-template <int ALAY, int BLAY, int EPI, int AMODE, int BMODE>
-int launch_cfg(Tcg2Args& a, cudaStream_t st) {
+// dry: only plan (tile width, resident B, ring depths -> a), no tensor maps, no launch
+template <int ALAY, int BLAY, int EPI, int AMODE, int BMODE, int EW = 8>
+int launch_cfg(Tcg2Args& a, cudaStream_t st, bool dry = false) {
+    constexpr int EPI_W = EW, EPI_SETS = EW / 4;
     // converter groups (several k-blocks in conversion at once) are an opt-in experiment: B200SP_TCG2_GROUPS=2|4.  Measured
     // (profiles/r2_gemm_variants.txt): +2-4 % on the long-M data-gradient shapes, nothing elsewhere, while the run-time group
     // geometry costs the single-group path 2.4x more converter instructions -- so the default instantiation has it compiled out.
     using E = ETf;
     static bool attr_set = false;
-    auto kern = tcgemm2_kernel<ALAY, BLAY, EPI, AMODE, BMODE, false>;
-    auto kern_g = tcgemm2_kernel<ALAY, BLAY, EPI == TCG_EPI_ATOMIC ? TCG_EPI_ATOMIC : EPI, AMODE, BMODE, EPI != TCG_EPI_ATOMIC>;
+    auto kern = tcgemm2_kernel<ALAY, BLAY, EPI, AMODE, BMODE, false, false, EW>;
+    // converter groups exist for the 16-converter-warp split only
+    auto kern_g = tcgemm2_kernel<ALAY, BLAY, EPI == TCG_EPI_ATOMIC ? TCG_EPI_ATOMIC : EPI, AMODE, BMODE, EPI != TCG_EPI_ATOMIC && EW == 8, false, EW>;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
         if (e == cudaSuccess && EPI != TCG_EPI_ATOMIC) e = cudaFuncSetAttribute(kern_g, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
@@ -854,7 +888,7 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st) {
     {
         static int ts_env = -1;
         if (ts_env < 0) { const char* e = getenv("B200SP_TCG2_TS"); ts_env = (e && e[0] == '1') ? 1 : 0; }
-        a.ts = (ts_env && ALAY == TCG_LAY_KM && a.R >= 8 && a.R % 8 == 0) ? 1 : 0;
+        a.ts = (ts_env && EW == 8 && ALAY == TCG_LAY_KM && a.R >= 8 && a.R % 8 == 0) ? 1 : 0;
     }
     // ---- tile width: the widest that fits shared memory; narrower while the grid does not cover the machine ----
     bool fits = false;
@@ -876,7 +910,7 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st) {
         const uint32_t bres_bytes = (uint32_t)a.nkb * a.nm * a.b_op_bytes;
         a.b_res = (EPI != TCG_EPI_ATOMIC && numQt == 1 && BMODE == XM_PLAIN && bres_bytes <= BRES_LIMIT) ? 1 : 0;
         a.op_stage_bytes = a.nm * ((a.ts ? 0 : a.a_op_bytes) + (a.b_res ? 0 : a.b_op_bytes));
-        a.raw_stage_bytes = (APT + (AMODE == XM_DY ? APT : 0) + (a.b_res ? 0 : nb_slots)) * 8192;
+        a.raw_stage_bytes = (A_SLOTS + (AMODE == XM_DY ? A_SLOTS : 0) + (a.b_res ? 0 : nb_slots)) * 8192;
         if (a.b_res && a.raw_stage_bytes < (uint32_t)nb_slots * 8192) a.raw_stage_bytes = nb_slots * 8192;
         const uint32_t fixed = EPI_W * 32 * STG_LD * 4 + EPI_W * 2 * BN * 4 + 512 + (a.b_res ? bres_bytes : 0);
         auto fit = [&](int nop, int nraw) { return nop * a.op_stage_bytes + nraw * a.raw_stage_bytes + fixed + 1088 <= SMEM_LIMIT; };
@@ -886,7 +920,7 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st) {
         // raw stages first (they hide the TMA latency and are the cheaper ones), operand stages after
         static int gmax = -1;
         if (gmax < 0) { const char* e = getenv("B200SP_TCG2_GROUPS"); gmax = e ? atoi(e) : 1; if (gmax != 1 && gmax != 2 && gmax != 4) gmax = 1; }
-        int G = (EPI == TCG_EPI_ATOMIC || a.ts) ? 1 : gmax;        // the TMEM A path deals one k-block to all 16 converter warps
+        int G = (EPI == TCG_EPI_ATOMIC || a.ts || EW != 8) ? 1 : gmax;        // the TMEM A path deals one k-block to all 16 converter warps
         while (G > 1 && !fit(G, G)) G >>= 1;
         if (G == 1) { a.n_op = 2; a.n_raw = 2; } else { a.n_op = G; a.n_raw = G; }
         a.groups = G;
@@ -928,10 +962,11 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st) {
         // MN-major B: the hi tile must end on an atom boundary for the lo tile to continue the N index
         a.stack_b = (sb && a.nm == 2 && a.acc_cols == 2 * BN && 2 * BN <= 256 && (BLAY == TCG_LAY_KM || BN % 32 == 0)) ? 1 : 0;
     }
-    a.split_epi = (BN <= 32 && numQt == 1 && EPI_SETS == 2) ? 1 : 0;
+    a.split_epi = (BN <= 32 && numQt == 1 && EPI_SETS >= 2) ? 1 : 0;
     uint32_t cols = 32;
     while (cols < (uint32_t)(a.nacc * a.acc_cols)) cols <<= 1;
     a.tmem_cols = a.ts ? 512u : cols;
+    if (dry) return 0;
     // ---- tensor maps of the raw operands ----
     int rc;
     if (ALAY == TCG_LAY_KM) { rc = encode_f32(&a.mapA, a.a.x, a.R, a.P, a.lda, BM, a.ts != 0); a.a_tx = BM * 128; }
@@ -953,7 +988,21 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st) {
     B200SP_RETURN_LAST();
 }
 
-constexpr int PRE_NT = EPI_T + MMA_T + TMA_T;
+// 16 epilogue warps need 37 KB more shared memory (staging tiles + statistics rows) than 8: taken only when that costs neither
+// tile width nor the resident weights (r3e: shapes that lost either ran 20-50 % slower than with 8 warps)
+template <int ALAY, int BLAY, int EPI, int AMODE, int BMODE>
+int launch_ew(Tcg2Args& a, cudaStream_t st, bool want16, bool force16) {
+    if (want16 && !force16) {
+        Tcg2Args a8 = a, a16 = a;
+        const int r8 = launch_cfg<ALAY, BLAY, EPI, AMODE, BMODE, 8>(a8, st, true);
+        const int r16 = launch_cfg<ALAY, BLAY, EPI, AMODE, BMODE, 16>(a16, st, true);
+        want16 = r8 == 0 && r16 == 0 && a16.BN == a8.BN && a16.b_res == a8.b_res;
+    }
+    if (want16) return launch_cfg<ALAY, BLAY, EPI, AMODE, BMODE, 16>(a, st);
+    return launch_cfg<ALAY, BLAY, EPI, AMODE, BMODE, 8>(a, st);
+}
+
+constexpr int PRE_NT = 8 * 32 + MMA_T + TMA_T;
 
 // planes [nm][rows][ld] of a presplit operand: {R, rows, nm} with a {32, box_rows, nm} box, 128-byte swizzle, zero fill
 inline int encode_planes(CUtensorMap* m, const float* base, int R, int rows, int ld, size_t plane, int nm, int box_rows) {
@@ -977,7 +1026,8 @@ inline long long pre_cost(int tiles, int kb_per_tile, int BN) {
 template <int EPI>
 int launch_pre(Tcg2Args& a, const float* A, int lda, size_t planeA, const float* B, int ldb, size_t planeB, cudaStream_t st) {
     using E = ETf;
-    auto kern = tcgemm2_kernel<TCG_LAY_KM, TCG_LAY_KM, EPI, XM_PLAIN, XM_PLAIN, false, true>;
+    constexpr int EPI_W = 8, EPI_SETS = 2;
+    auto kern = tcgemm2_kernel<TCG_LAY_KM, TCG_LAY_KM, EPI, XM_PLAIN, XM_PLAIN, false, true, 8>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
@@ -1030,7 +1080,7 @@ int launch_pre(Tcg2Args& a, const float* A, int lda, size_t planeA, const float*
     a.acc_cols = (a.nm == 2 && 2 * 2 * BN <= 512) ? 2 * BN : BN;
     a.nacc = 4 * a.acc_cols <= 512 ? 4 : 2;
     a.stack_b = (a.nm == 2 && a.acc_cols == 2 * BN && 2 * BN <= 256) ? 1 : 0;
-    a.split_epi = (BN <= 32 && numQt == 1 && EPI_SETS == 2) ? 1 : 0;
+    a.split_epi = (BN <= 32 && numQt == 1 && EPI_SETS >= 2) ? 1 : 0;
     uint32_t cols = 32;
     while (cols < (uint32_t)(a.nacc * a.acc_cols)) cols <<= 1;
     a.tmem_cols = cols;
@@ -1154,13 +1204,23 @@ int tcgemm2_launch(const TcgProblem& p, cudaStream_t st) {
     a.epi_sleep = 512;
     a.nm = p.dtype == B200SP_F32_TF32X1 ? 1 : 2;
     const int am = p.a.mode, bm = p.b.mode;
+    // short reduction (<= B200SP_TCG2_EW_R, default 32 = one k-block): the epilogue bounds the kernel -> 16 epilogue warps
+    // (r3f: +15 % on fwd [602112,96,16], +23 % on dgrad [602112,16,32]; longer reductions lose 5-15 % to the halved converter)
+    static int ew_env = -1, ew_r = 32;
+    if (ew_env < 0) {
+        const char* e = getenv("B200SP_TCG2_EW");
+        ew_env = e ? atoi(e) : 0;                   // 0 auto | 8 | 16
+        const char* r = getenv("B200SP_TCG2_EW_R");
+        if (r) ew_r = atoi(r);
+    }
+    const bool ew16 = ew_env == 16 || (ew_env == 0 && p.R <= ew_r);
     if (p.epi == TCG_EPI_FWD && p.a_lay == TCG_LAY_KM && p.b_lay == TCG_LAY_KM && bm == B200SP_VT_PLAIN) {
-        if (am == B200SP_VT_PLAIN) return launch_cfg<TCG_LAY_KM, TCG_LAY_KM, TCG_EPI_FWD, XM_PLAIN, XM_PLAIN>(a, st);
-        if (am == B200SP_VT_BNACT) return launch_cfg<TCG_LAY_KM, TCG_LAY_KM, TCG_EPI_FWD, XM_BNACT, XM_PLAIN>(a, st);
+        if (am == B200SP_VT_PLAIN) return launch_ew<TCG_LAY_KM, TCG_LAY_KM, TCG_EPI_FWD, XM_PLAIN, XM_PLAIN>(a, st, ew16, ew_env == 16);
+        if (am == B200SP_VT_BNACT) return launch_ew<TCG_LAY_KM, TCG_LAY_KM, TCG_EPI_FWD, XM_BNACT, XM_PLAIN>(a, st, ew16, ew_env == 16);
     }
     if (p.epi == TCG_EPI_DGRAD && p.a_lay == TCG_LAY_KM && p.b_lay == TCG_LAY_MM && bm == B200SP_VT_PLAIN) {
-        if (am == B200SP_VT_PLAIN) return launch_cfg<TCG_LAY_KM, TCG_LAY_MM, TCG_EPI_DGRAD, XM_PLAIN, XM_PLAIN>(a, st);
-        if (am == B200SP_VT_DY) return launch_cfg<TCG_LAY_KM, TCG_LAY_MM, TCG_EPI_DGRAD, XM_DY, XM_PLAIN>(a, st);
+        if (am == B200SP_VT_PLAIN) return launch_ew<TCG_LAY_KM, TCG_LAY_MM, TCG_EPI_DGRAD, XM_PLAIN, XM_PLAIN>(a, st, ew16, ew_env == 16);
+        if (am == B200SP_VT_DY) return launch_ew<TCG_LAY_KM, TCG_LAY_MM, TCG_EPI_DGRAD, XM_DY, XM_PLAIN>(a, st, ew16, ew_env == 16);
     }
     if (p.epi == TCG_EPI_ATOMIC && p.a_lay == TCG_LAY_MM && p.b_lay == TCG_LAY_MM) {
         if (am == B200SP_VT_PLAIN && bm == B200SP_VT_PLAIN) return launch_cfg<TCG_LAY_MM, TCG_LAY_MM, TCG_EPI_ATOMIC, XM_PLAIN, XM_PLAIN>(a, st);
