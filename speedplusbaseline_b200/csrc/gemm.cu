@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "tcgemm.cuh"
 
+int wgdirect_launch(const b200sp_vtensor* dy, const b200sp_vtensor* x, float* dw, int M, int N, int K, cudaStream_t st);   // wgdirect.cu
 int pwdirect_fwd(const b200sp_vtensor* x, const float* w, const float* bias, int out_act, float* y, const b200sp_bnfwd* bn,
                  int M, int N, int K, cudaStream_t st);       // pwdirect.cu
 int pwdirect_dgrad(const b200sp_vtensor* dy, const float* w, const float* skip, float scale_out, float* g, const b200sp_bnbwd* bn,
@@ -431,6 +432,11 @@ extern "C" int b200sp_pw_dgrad(const b200sp_vtensor* dy, const float* w, const v
 extern "C" int b200sp_pw_wgrad(const b200sp_vtensor* dy, const b200sp_vtensor* x, float* dw, float* dbias,
                                int M, int N, int K, int dtype, void* stream) {
     if (!dy || !x || x->mode == B200SP_VT_DY) return B200SP_EINVAL;
+    if (dtype == B200SP_F32 || dtype == B200SP_F32_TF32X1) {      // long-M / tiny-N*K layers: streaming fp32 reduction (wgdirect.cu)
+        const int rc = wgdirect_launch(dy, x, dw, M, N, K, (cudaStream_t)stream);
+        if (rc == 0 && dbias) return b200sp_colsum_f32(dy, dbias, M, N, B200SP_F32, stream);
+        if (rc != B200SP_ENOSYS) return rc;
+    }
     if (dtype == B200SP_F32_TF32X1) {
         TcgProblem p = {};
         p.a = *dy; p.b = *x; p.a_lay = TCG_LAY_MM; p.b_lay = TCG_LAY_MM;

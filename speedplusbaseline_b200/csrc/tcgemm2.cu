@@ -870,10 +870,10 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st, bool dry = false) {
     static bool attr_set = false;
     auto kern = tcgemm2_kernel<ALAY, BLAY, EPI, AMODE, BMODE, false, false, EW>;
     // converter groups exist for the 16-converter-warp split only
-    auto kern_g = tcgemm2_kernel<ALAY, BLAY, EPI == TCG_EPI_ATOMIC ? TCG_EPI_ATOMIC : EPI, AMODE, BMODE, EPI != TCG_EPI_ATOMIC && EW == 8, false, EW>;
+    auto kern_g = tcgemm2_kernel<ALAY, BLAY, EPI, AMODE, BMODE, EW == 8, false, EW>;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
-        if (e == cudaSuccess && EPI != TCG_EPI_ATOMIC) e = cudaFuncSetAttribute(kern_g, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_g, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
@@ -920,7 +920,9 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st, bool dry = false) {
         // raw stages first (they hide the TMA latency and are the cheaper ones), operand stages after
         static int gmax = -1;
         if (gmax < 0) { const char* e = getenv("B200SP_TCG2_GROUPS"); gmax = e ? atoi(e) : 1; if (gmax != 1 && gmax != 2 && gmax != 4) gmax = 1; }
-        int G = (EPI == TCG_EPI_ATOMIC || a.ts || EW != 8) ? 1 : gmax;        // the TMEM A path deals one k-block to all 16 converter warps
+        static int gmax_wg = -1;      // weight gradient: its own switch (B200SP_TCG2_WG_GROUPS)
+        if (gmax_wg < 0) { const char* e = getenv("B200SP_TCG2_WG_GROUPS"); gmax_wg = e ? atoi(e) : 1; if (gmax_wg != 1 && gmax_wg != 2 && gmax_wg != 4) gmax_wg = 1; }
+        int G = (a.ts || EW != 8) ? 1 : (EPI == TCG_EPI_ATOMIC ? gmax_wg : gmax);        // the TMEM A path deals one k-block to all 16 converter warps
         while (G > 1 && !fit(G, G)) G >>= 1;
         if (G == 1) { a.n_op = 2; a.n_raw = 2; } else { a.n_op = G; a.n_raw = G; }
         a.groups = G;

@@ -130,6 +130,34 @@ def test_pw_wgrad(M, N, K):
     assert rel(db, dy.sum(0)) < 1e-5
 
 
+@pytest.mark.parametrize('M,N,K', [(70001, 16, 32), (65537, 24, 144), (80004, 96, 24), (66001, 192, 32), (65536, 32, 192), (70000, 24, 96),
+                                   (602112, 16, 32), (150528, 24, 144)])
+@pytest.mark.parametrize('dy_mode,x_mode', [('dy', 'bnact'), ('plain', 'plain'), ('dy', 'plain'), ('plain', 'bnact')])
+def test_pw_wgrad_streaming_reduction(M, N, K, dy_mode, x_mode):
+    """wgdirect.cu: the long-M / tiny-N*K weight gradients as an fp32 streaming reduction (M >= 65536, N*K <= 6144, N <= 4 K;
+    the (96, 24) case stays on the tensor-core kernel): every operand-mode combination, ragged M (last slab partial),
+    accumulation into a non-zero dW, one launch per call."""
+    if M > 200000 and (dy_mode, x_mode) != ('dy', 'bnact'):
+        pytest.skip('full size once')
+    g = _g(M + 3 * N + K)
+    gq, yq = torch.randn(M, N, generator=g), torch.randn(M, N, generator=g)
+    cA, cB, cC = torch.rand(N, generator=g) + 0.5, torch.randn(N, generator=g) * 0.1, torch.randn(N, generator=g) * 0.1
+    x = torch.randn(M, K, generator=g)
+    sc, sh = torch.rand(K, generator=g) + 0.5, torch.randn(K, generator=g)
+    dy = cA.double() * gq.double() + cB.double() * yq.double() + cC.double() if dy_mode == 'dy' else gq.double()
+    xin = F.leaky_relu(x.double() * sc.double() + sh.double(), 0.2) if x_mode == 'bnact' else x.double()
+    ref = dy.t() @ xin
+    dw = torch.full((N, K), -0.25, device='cuda')
+    t = [v.cuda() for v in (gq, yq, cA, cB, cC, x, sc, sh)]
+    a = vt_dy(*t[:5]) if dy_mode == 'dy' else vt_plain(t[0])
+    b = vt_bnact(t[5], t[6], t[7], L.ACT_LEAKY02) if x_mode == 'bnact' else vt_plain(t[5])
+    n0 = L.lib.b200sp_launch_count()
+    L.call('b200sp_pw_wgrad', C.byref(a), C.byref(b), dw.data_ptr(), None, M, N, K, L.F32, sp())
+    torch.cuda.synchronize()
+    assert L.lib.b200sp_launch_count() - n0 == 1
+    assert rel(dw + 0.25, ref) < 2e-5
+
+
 @pytest.mark.parametrize('B,H,W,Cc,s', [(2, 13, 9, 32, 1), (3, 14, 14, 144, 2), (2, 7, 7, 1280, 1), (1, 33, 20, 96, 2), (2, 56, 56, 24, 1)])
 def test_dw_fwd(B, H, W, Cc, s):
     g = _g(H * W + Cc + s)
