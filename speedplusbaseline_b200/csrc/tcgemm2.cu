@@ -40,7 +40,9 @@ namespace {
 //            instructions per warp (~12 cycles per instruction, schedulers 17 % busy: r3d ncu capture of dgrad [150528,24,144]),
 //            so it scales with the number of warps draining chunks while the converters sit idle 70 % of the time
 constexpr int MMA_T = 32, TMA_T = 32;
-constexpr int NT = 832;
+//   EW =  8, PW = 8 (576 threads): the register file then allows 112 registers per thread instead of 72 -- the data-gradient epilogue
+//            (32 accumulator values + BatchNorm-backward operands per lane) spills and rematerialises addresses at 72
+__host__ __device__ constexpr int nt_of(int ew, int pw) { return (ew + 2 + pw) * 32; }
 constexpr int A_SLOTS = 2;                      // 8192-byte sub-slots of a raw 128-row x 128-byte tile
 constexpr int BM = 128;
 constexpr int STG_LD = 36;
@@ -291,8 +293,9 @@ __device__ __forceinline__ void tma_operand(uint32_t dst, const CUtensorMap* m, 
 // =====================================================================================================
 // PRE: the operands arrive pre-split (opsplit.cu): K-major planes [hi | lo] that the TMA unit loads straight into the swizzled
 // operand ring -- no raw ring, no converter warps (the kernel is launched with the first PRE_NT threads only).
-template <int ALAY, int BLAY, int EPI, int AMODE, int BMODE, bool GRP, bool PRE = false, int EW = 8>
-__global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ Tcg2Args g) {
+template <int ALAY, int BLAY, int EPI, int AMODE, int BMODE, bool GRP, bool PRE = false, int EW = 8, int PW = 24 - EW>
+__global__ void __launch_bounds__(nt_of(EW, PW), 1) tcgemm2_kernel(const __grid_constant__ Tcg2Args g) {
+    constexpr int NT = nt_of(EW, PW);
     using T = float;
     using E = ETf;
     constexpr int EPI_W = EW, EPI_T = EW * 32, EPI_SETS = EW / 4, MMA_WARP = EW, TMA_WARP = EW + 1;
@@ -697,7 +700,7 @@ __global__ void __launch_bounds__(NT, 1) tcgemm2_kernel(const __grid_constant__ 
 #pragma unroll
                     for (int i = 0; i < 16; ++i) { r[i] = r16[i]; r[16 + i] = 0u; }
                 }
-                constexpr bool MERGE_LD = EPI != TCG_EPI_DGRAD;      // the dgrad epilogue is register-bound: it keeps the loads apart
+                constexpr bool MERGE_LD = EPI != TCG_EPI_DGRAD || NT <= 576;      // the dgrad epilogue is register-bound at 72 registers: it keeps the loads apart
                 if (MERGE_LD && split_acc) tc::tmem_ld16(t_row + g.BN + c0, q16);
                 tc::tmem_ld_wait();
                 if (tid == 0) { TL(10, tle); ++tle; }
@@ -860,17 +863,17 @@ inline int encode_f32(CUtensorMap* m, const void* base, int cols, int rows, int 
 }
 
 // dry: only plan (tile width, resident B, ring depths -> a), no tensor maps, no launch
-template <int ALAY, int BLAY, int EPI, int AMODE, int BMODE, int EW = 8>
+template <int ALAY, int BLAY, int EPI, int AMODE, int BMODE, int EW = 8, int PW = 24 - EW>
 int launch_cfg(Tcg2Args& a, cudaStream_t st, bool dry = false) {
-    constexpr int EPI_W = EW, EPI_SETS = EW / 4;
+    constexpr int EPI_W = EW, EPI_SETS = EW / 4, NT = nt_of(EW, PW);
     // converter groups (several k-blocks in conversion at once) are an opt-in experiment: B200SP_TCG2_GROUPS=2|4.  Measured
     // (profiles/r2_gemm_variants.txt): +2-4 % on the long-M data-gradient shapes, nothing elsewhere, while the run-time group
     // geometry costs the single-group path 2.4x more converter instructions -- so the default instantiation has it compiled out.
     using E = ETf;
     static bool attr_set = false;
-    auto kern = tcgemm2_kernel<ALAY, BLAY, EPI, AMODE, BMODE, false, false, EW>;
+    auto kern = tcgemm2_kernel<ALAY, BLAY, EPI, AMODE, BMODE, false, false, EW, PW>;
     // converter groups exist for the 16-converter-warp split only
-    auto kern_g = tcgemm2_kernel<ALAY, BLAY, EPI, AMODE, BMODE, EW == 8, false, EW>;
+    auto kern_g = tcgemm2_kernel<ALAY, BLAY, EPI, AMODE, BMODE, EW == 8 && PW == 16, false, EW, PW>;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_g, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
@@ -888,7 +891,7 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st, bool dry = false) {
     {
         static int ts_env = -1;
         if (ts_env < 0) { const char* e = getenv("B200SP_TCG2_TS"); ts_env = (e && e[0] == '1') ? 1 : 0; }
-        a.ts = (ts_env && EW == 8 && ALAY == TCG_LAY_KM && a.R >= 8 && a.R % 8 == 0) ? 1 : 0;
+        a.ts = (ts_env && EW == 8 && PW == 16 && ALAY == TCG_LAY_KM && a.R >= 8 && a.R % 8 == 0) ? 1 : 0;
     }
     // ---- tile width: the widest that fits shared memory; narrower while the grid does not cover the machine ----
     bool fits = false;
@@ -922,7 +925,7 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st, bool dry = false) {
         if (gmax < 0) { const char* e = getenv("B200SP_TCG2_GROUPS"); gmax = e ? atoi(e) : 1; if (gmax != 1 && gmax != 2 && gmax != 4) gmax = 1; }
         static int gmax_wg = -1;      // weight gradient: its own switch (B200SP_TCG2_WG_GROUPS)
         if (gmax_wg < 0) { const char* e = getenv("B200SP_TCG2_WG_GROUPS"); gmax_wg = e ? atoi(e) : 1; if (gmax_wg != 1 && gmax_wg != 2 && gmax_wg != 4) gmax_wg = 1; }
-        int G = (a.ts || EW != 8) ? 1 : (EPI == TCG_EPI_ATOMIC ? gmax_wg : gmax);        // the TMEM A path deals one k-block to all 16 converter warps
+        int G = (a.ts || EW != 8 || PW != 16) ? 1 : (EPI == TCG_EPI_ATOMIC ? gmax_wg : gmax);        // the TMEM A path deals one k-block to all 16 converter warps
         while (G > 1 && !fit(G, G)) G >>= 1;
         if (G == 1) { a.n_op = 2; a.n_raw = 2; } else { a.n_op = G; a.n_raw = G; }
         a.groups = G;
@@ -993,7 +996,10 @@ int launch_cfg(Tcg2Args& a, cudaStream_t st, bool dry = false) {
 // 16 epilogue warps need 37 KB more shared memory (staging tiles + statistics rows) than 8: taken only when that costs neither
 // tile width nor the resident weights (r3e: shapes that lost either ran 20-50 % slower than with 8 warps)
 template <int ALAY, int BLAY, int EPI, int AMODE, int BMODE>
-int launch_ew(Tcg2Args& a, cudaStream_t st, bool want16, bool force16) {
+int launch_ew(Tcg2Args& a, cudaStream_t st, bool want16, bool force16, bool lean = false) {
+    // measured on the whole step (r3n / r3o): 8 + 8 warps 5.66 ms; 8 + 4 warps (144 registers) 5.71; 8 + 16 (72 registers) 5.78;
+    // the weight-gradient kernel (main-loop-bound) loses 0.06 ms with 8 converter warps and keeps 16
+    if (lean) return launch_cfg<ALAY, BLAY, EPI, AMODE, BMODE, 8, 8>(a, st);
     if (want16 && !force16) {
         Tcg2Args a8 = a, a16 = a;
         const int r8 = launch_cfg<ALAY, BLAY, EPI, AMODE, BMODE, 8>(a8, st, true);
@@ -1216,13 +1222,22 @@ int tcgemm2_launch(const TcgProblem& p, cudaStream_t st) {
         if (r) ew_r = atoi(r);
     }
     const bool ew16 = ew_env == 16 || (ew_env == 0 && p.R <= ew_r);
+    // 576-thread variant (8 epilogue + 8 converter warps, 112 registers per thread): B200SP_TCG2_LEAN = dgrad | all, reduction <= LEAN_R
+    static int lean_mode = -1, lean_r = 1 << 30;
+    if (lean_mode < 0) {
+        const char* e = getenv("B200SP_TCG2_LEAN");
+        lean_mode = !e ? 2 : (e[0] == 'd' ? 1 : (e[0] == 'a' ? 2 : 0));       // default: all (r3n: KRN step 5.78 -> 5.66 ms)
+        const char* r = getenv("B200SP_TCG2_LEAN_R");
+        if (r) lean_r = atoi(r);
+    }
+    const bool lean_d = lean_mode >= 1 && p.R <= lean_r, lean_f = lean_mode == 2 && p.R <= lean_r;
     if (p.epi == TCG_EPI_FWD && p.a_lay == TCG_LAY_KM && p.b_lay == TCG_LAY_KM && bm == B200SP_VT_PLAIN) {
-        if (am == B200SP_VT_PLAIN) return launch_ew<TCG_LAY_KM, TCG_LAY_KM, TCG_EPI_FWD, XM_PLAIN, XM_PLAIN>(a, st, ew16, ew_env == 16);
-        if (am == B200SP_VT_BNACT) return launch_ew<TCG_LAY_KM, TCG_LAY_KM, TCG_EPI_FWD, XM_BNACT, XM_PLAIN>(a, st, ew16, ew_env == 16);
+        if (am == B200SP_VT_PLAIN) return launch_ew<TCG_LAY_KM, TCG_LAY_KM, TCG_EPI_FWD, XM_PLAIN, XM_PLAIN>(a, st, ew16, ew_env == 16, lean_f);
+        if (am == B200SP_VT_BNACT) return launch_ew<TCG_LAY_KM, TCG_LAY_KM, TCG_EPI_FWD, XM_BNACT, XM_PLAIN>(a, st, ew16, ew_env == 16, lean_f);
     }
     if (p.epi == TCG_EPI_DGRAD && p.a_lay == TCG_LAY_KM && p.b_lay == TCG_LAY_MM && bm == B200SP_VT_PLAIN) {
-        if (am == B200SP_VT_PLAIN) return launch_ew<TCG_LAY_KM, TCG_LAY_MM, TCG_EPI_DGRAD, XM_PLAIN, XM_PLAIN>(a, st, ew16, ew_env == 16);
-        if (am == B200SP_VT_DY) return launch_ew<TCG_LAY_KM, TCG_LAY_MM, TCG_EPI_DGRAD, XM_DY, XM_PLAIN>(a, st, ew16, ew_env == 16);
+        if (am == B200SP_VT_PLAIN) return launch_ew<TCG_LAY_KM, TCG_LAY_MM, TCG_EPI_DGRAD, XM_PLAIN, XM_PLAIN>(a, st, ew16, ew_env == 16, lean_d);
+        if (am == B200SP_VT_DY) return launch_ew<TCG_LAY_KM, TCG_LAY_MM, TCG_EPI_DGRAD, XM_DY, XM_PLAIN>(a, st, ew16, ew_env == 16, lean_d);
     }
     if (p.epi == TCG_EPI_ATOMIC && p.a_lay == TCG_LAY_MM && p.b_lay == TCG_LAY_MM) {
         if (am == B200SP_VT_PLAIN && bm == B200SP_VT_PLAIN) return launch_cfg<TCG_LAY_MM, TCG_LAY_MM, TCG_EPI_ATOMIC, XM_PLAIN, XM_PLAIN>(a, st);
