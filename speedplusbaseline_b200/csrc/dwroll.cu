@@ -430,8 +430,10 @@ __device__ __forceinline__ float4 bwd2_finish(float4 dg, float4 yin, float4 z, f
     return dg;
 }
 
-template <int S, int ACT>
-__global__ void __launch_bounds__(RNT, S == 2 ? 4 : DWR_S1_OCC) dwr_bwd2_kernel(const b200sp_vtensor dy, const float* __restrict__ w9c,
+// PF (stride 1): the raw loads of the NEXT row step are issued before the current step's arithmetic (register double buffer,
+// 2 CTAs per SM instead of 3) -- without it a thread's loads and its ~200 dependent instructions per row strictly alternate.
+template <int S, int ACT, bool PF = false>
+__global__ void __launch_bounds__(RNT, PF ? (S == 2 ? 3 : 2) : (S == 2 ? 4 : DWR_S1_OCC)) dwr_bwd2_kernel(const b200sp_vtensor dy, const float* __restrict__ w9c,
                                                           float* __restrict__ g_in, float* __restrict__ dw9c,
                                                           const b200sp_bnbwd bn, const RGeom gm) {
     extern __shared__ __align__(16) unsigned char bwd2_smem[];
@@ -471,14 +473,28 @@ __global__ void __launch_bounds__(RNT, S == 2 ? 4 : DWR_S1_OCC) dwr_bwd2_kernel(
             int od = ((it.b * gm.Ho + it.r_a) * gm.Wo + cb) * C + c;       // dy(a, cb)
             int ox = ((it.b * gm.H + 2 * it.r_a) * gm.W + 2 * cb) * C + c; // input (2a, 2cb)
             float4 E00 = dyv(od, 1.f), E01 = dyv(od + dcol, m1);
+            float4 pf[8];                                  // PF: raw g10 y10 g11 y11 yi0..yi3 of the step about to run
+            auto fetch = [&](int a, int od_, int ox_, float4 (&q)[8]) {
+                const int odn = od_ + (a + 1 < gm.Ho ? drow : 0), oxh = ox_ + (2 * a + 1 < gm.H ? xrow : 0);
+                q[0] = ldf4(gq + odn); q[1] = ldf4(yq + odn); q[2] = ldf4(gq + odn + dcol); q[3] = ldf4(yq + odn + dcol);
+                q[4] = ldf4(yb + ox_); q[5] = ldf4(yb + ox_ + xcol); q[6] = ldf4(yb + oxh); q[7] = ldf4(yb + oxh + xcol);
+            };
+            if (PF) fetch(it.r_a, od, ox, pf);
             for (int a = it.r_a; a < it.r_b; ++a) {
                 const bool r1 = a + 1 < gm.Ho, h1 = 2 * a + 1 < gm.H;
-                const int odn = od + (r1 ? drow : 0);
                 const float mr = r1 ? 1.f : 0.f;
-                // all loads of the step first
-                const float4 g10 = ldf4(gq + odn), y10 = ldf4(yq + odn), g11 = ldf4(gq + odn + dcol), y11 = ldf4(yq + odn + dcol);
                 const int oxh = ox + (h1 ? xrow : 0);
-                const float4 yi0 = ldf4(yb + ox), yi1 = ldf4(yb + ox + xcol), yi2 = ldf4(yb + oxh), yi3 = ldf4(yb + oxh + xcol);
+                // all loads of the step first (PF: they were issued one step ago; the next step's go out now)
+                float4 cur[8];
+                if (PF) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) cur[j] = pf[j];
+                    if (a + 1 < it.r_b) fetch(a + 1, od + drow, ox + 2 * xrow, pf);
+                } else {
+                    fetch(a, od, ox, cur);
+                }
+                const float4 g10 = cur[0], y10 = cur[1], g11 = cur[2], y11 = cur[3];
+                const float4 yi0 = cur[4], yi1 = cur[5], yi2 = cur[6], yi3 = cur[7];
                 const float4 E10 = f4scale(f4fma(cA, g10, f4fma(cB, y10, cC)), mr);
                 const float4 E11 = f4scale(f4fma(cA, g11, f4fma(cB, y11, cC)), mr * m1);
                 {   // (ph, pw) = (0, 0): tap 4
@@ -539,14 +555,34 @@ __global__ void __launch_bounds__(RNT, S == 2 ? 4 : DWR_S1_OCC) dwr_bwd2_kernel(
             dyrow(it.r_a, D1);
             int ox = ((it.b * gm.H + it.r_a) * gm.W + wi0) * C + c;
             const int xcol = p1 ? C : 0, xrow = gm.W * C;
+            float4 pg[4], py[4], pyi0, pyi1;              // PF: raw values of the step about to run
+            if (PF) {
+                const int o = dbase + min(it.r_a + 1, gm.Ho - 1) * drow;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { pg[j] = ldf4(gq + o + dco[j]); py[j] = ldf4(yq + o + dco[j]); }
+                pyi0 = ldf4(yb + ox); pyi1 = ldf4(yb + ox + xcol);
+            }
             for (int hi = it.r_a; hi < it.r_b; ++hi) {
                 const int rn = hi + 1;
                 const float mr = rn < gm.Ho ? 1.f : 0.f;
                 const int o = dbase + min(rn, gm.Ho - 1) * drow;
                 float4 g[4], y[4];
+                float4 yi0, yi1;
+                if (PF) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { g[j] = ldf4(gq + o + dco[j]); y[j] = ldf4(yq + o + dco[j]); }
-                const float4 yi0 = ldf4(yb + ox), yi1 = ldf4(yb + ox + xcol);
+                    for (int j = 0; j < 4; ++j) { g[j] = pg[j]; y[j] = py[j]; }
+                    yi0 = pyi0; yi1 = pyi1;
+                    if (hi + 1 < it.r_b) {                  // next step: dy row hi + 2 (clamped), input row hi + 1
+                        const int o2 = dbase + min(rn + 1, gm.Ho - 1) * drow;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { pg[j] = ldf4(gq + o2 + dco[j]); py[j] = ldf4(yq + o2 + dco[j]); }
+                        pyi0 = ldf4(yb + ox + xrow); pyi1 = ldf4(yb + ox + xrow + xcol);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { g[j] = ldf4(gq + o + dco[j]); y[j] = ldf4(yq + o + dco[j]); }
+                    yi0 = ldf4(yb + ox); yi1 = ldf4(yb + ox + xcol);
+                }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) D2[j] = f4scale(f4fma(cA, g[j], f4fma(cB, y[j], cC)), mr * mc[j]);
 #pragma unroll
@@ -615,8 +651,8 @@ struct Fwd2Shared {
     float4 s1[RNT], s2[RNT];
 };
 
-template <int S, int ACT>
-__global__ void __launch_bounds__(RNT, S == 2 ? 4 : DWR_S1_OCC) dwr_fwd2_kernel(const b200sp_vtensor x, const float* __restrict__ w9c,
+template <int S, int ACT, bool PF = false>
+__global__ void __launch_bounds__(RNT, PF ? (S == 2 ? 3 : 2) : (S == 2 ? 4 : DWR_S1_OCC)) dwr_fwd2_kernel(const b200sp_vtensor x, const float* __restrict__ w9c,
                                                                        float* __restrict__ y, const b200sp_bnfwd bn, const RGeom gm) {
     constexpr int OW = S == 1 ? 4 : 2;
     constexpr int NC = (OW - 1) * S + 3;
@@ -659,13 +695,32 @@ __global__ void __launch_bounds__(RNT, S == 2 ? 4 : DWR_S1_OCC) dwr_fwd2_kernel(
                 r[j] = f4scale(make_float4(actf2<ACT>(z.x), actf2<ACT>(z.y), actf2<ACT>(z.z), actf2<ACT>(z.w)), mr * mc[j]);
             }
         };
+        auto rawrow = [&](int row, float4 (&raw)[NC]) {        // PF: issue only; validity is applied when the row is consumed
+            const int o = xbase + min(max(row, 0), gm.H - 1) * xrow;
+#pragma unroll
+            for (int j = 0; j < NC; ++j) raw[j] = ldf4(xq + o + xco[j]);
+        };
+        auto finrow = [&](int row, const float4 (&raw)[NC], float4 (&r)[NC]) {
+            const float mr = (row >= 0 && row < gm.H) ? 1.f : 0.f;
+#pragma unroll
+            for (int j = 0; j < NC; ++j) {
+                const float4 z = f4fma(raw[j], sc, shf);
+                r[j] = f4scale(make_float4(actf2<ACT>(z.x), actf2<ACT>(z.y), actf2<ACT>(z.z), actf2<ACT>(z.w)), mr * mc[j]);
+            }
+        };
         float4 r0[NC], r1[NC], r2[NC];
-        if (S == 1) { loadrow(it.r_a - 1, r0); loadrow(it.r_a, r1); }
-        else        { loadrow(2 * it.r_a - 1, r0); }
+        float4 nx[NC], nx2[S == 2 ? NC : 1];
+        if (S == 1) { loadrow(it.r_a - 1, r0); loadrow(it.r_a, r1); if (PF) rawrow(it.r_a + 1, nx); }
+        else        { loadrow(2 * it.r_a - 1, r0); if (PF) { rawrow(2 * it.r_a, nx); rawrow(2 * it.r_a + 1, reinterpret_cast<float4(&)[NC]>(nx2)); } }
         int oy = ((it.b * gm.Ho + it.r_a) * gm.Wo + wo0) * C + c;
         const int yrow = gm.Wo * C;
         for (int ho = it.r_a; ho < it.r_b; ++ho) {
-            if (S == 1) { loadrow(ho + 1, r2); }
+            if (S == 1 && PF) { finrow(ho + 1, nx, r2); if (ho + 1 < it.r_b) rawrow(ho + 2, nx); }
+            else if (S == 1) { loadrow(ho + 1, r2); }
+            else if (PF) {
+                finrow(2 * ho, nx, r1); finrow(2 * ho + 1, reinterpret_cast<float4(&)[NC]>(nx2), r2);
+                if (ho + 1 < it.r_b) { rawrow(2 * ho + 2, nx); rawrow(2 * ho + 3, reinterpret_cast<float4(&)[NC]>(nx2)); }
+            }
             else        { loadrow(2 * ho, r1); loadrow(2 * ho + 1, r2); }
 #pragma unroll
             for (int o = 0; o < OW; ++o) {
@@ -741,6 +796,12 @@ inline bool use_roll() {
     return v == 1;
 }
 
+inline int dw_prefetch() {         // B200SP_DW_PF: 0 none | 1 stride-1 kernels (default) | 2 stride-2 kernels as well
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("B200SP_DW_PF"); v = !e ? 1 : (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1)); }
+    return v;
+}
+
 inline bool use_bwd2() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("B200SP_DW"); v = (e && e[0] == '1') ? 0 : 1; }      // second-generation kernels by default (validated on B200 in round 2: -0.4 ms/step); B200SP_DW=1 selects the first generation
@@ -759,9 +820,15 @@ int launch_fwd(const b200sp_vtensor* x, const float* w9c, void* y, const b200sp_
     if (use_bwd2() && sizeof(T) == 4 && bn && x->mode == B200SP_VT_BNACT && (x->act == B200SP_ACT_RELU6 || x->act == B200SP_ACT_RELU) &&
         (long long)B * H * W * C < (1ll << 31)) {
         const bool r6 = x->act == B200SP_ACT_RELU6;
-        if (stride == 1) {
+        if (stride == 1 && dw_prefetch()) {
+            if (r6) b200sp_launch_pdl(dwr_fwd2_kernel<1, B200SP_ACT_RELU6, true>, grid, dim3(RNT), 0, st, *x, w9c, (float*)y, b, gm);
+            else    b200sp_launch_pdl(dwr_fwd2_kernel<1, B200SP_ACT_RELU, true>, grid, dim3(RNT), 0, st, *x, w9c, (float*)y, b, gm);
+        } else if (stride == 1) {
             if (r6) b200sp_launch_pdl(dwr_fwd2_kernel<1, B200SP_ACT_RELU6>, grid, dim3(RNT), 0, st, *x, w9c, (float*)y, b, gm);
             else    b200sp_launch_pdl(dwr_fwd2_kernel<1, B200SP_ACT_RELU>, grid, dim3(RNT), 0, st, *x, w9c, (float*)y, b, gm);
+        } else if (dw_prefetch() == 2) {
+            if (r6) b200sp_launch_pdl(dwr_fwd2_kernel<2, B200SP_ACT_RELU6, true>, grid, dim3(RNT), 0, st, *x, w9c, (float*)y, b, gm);
+            else    b200sp_launch_pdl(dwr_fwd2_kernel<2, B200SP_ACT_RELU, true>, grid, dim3(RNT), 0, st, *x, w9c, (float*)y, b, gm);
         } else {
             if (r6) b200sp_launch_pdl(dwr_fwd2_kernel<2, B200SP_ACT_RELU6>, grid, dim3(RNT), 0, st, *x, w9c, (float*)y, b, gm);
             else    b200sp_launch_pdl(dwr_fwd2_kernel<2, B200SP_ACT_RELU>, grid, dim3(RNT), 0, st, *x, w9c, (float*)y, b, gm);
@@ -801,12 +868,22 @@ int launch_bwd(const b200sp_vtensor* dy, const b200sp_vtensor* x, const float* w
             cudaFuncSetAttribute(dwr_bwd2_kernel<2, B200SP_ACT_RELU6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             cudaFuncSetAttribute(dwr_bwd2_kernel<1, B200SP_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             cudaFuncSetAttribute(dwr_bwd2_kernel<2, B200SP_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cudaFuncSetAttribute(dwr_bwd2_kernel<1, B200SP_ACT_RELU6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cudaFuncSetAttribute(dwr_bwd2_kernel<1, B200SP_ACT_RELU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cudaFuncSetAttribute(dwr_bwd2_kernel<2, B200SP_ACT_RELU6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cudaFuncSetAttribute(dwr_bwd2_kernel<2, B200SP_ACT_RELU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             attr_set = true;
         }
         const bool r6 = bn->act == B200SP_ACT_RELU6;
-        if (stride == 1) {
+        if (stride == 1 && dw_prefetch()) {
+            if (r6) b200sp_launch_pdl(dwr_bwd2_kernel<1, B200SP_ACT_RELU6, true>, grid, dim3(RNT), smem, st, *dy, w9c, (float*)g_in, dw9c, b, gm);
+            else    b200sp_launch_pdl(dwr_bwd2_kernel<1, B200SP_ACT_RELU, true>, grid, dim3(RNT), smem, st, *dy, w9c, (float*)g_in, dw9c, b, gm);
+        } else if (stride == 1) {
             if (r6) b200sp_launch_pdl(dwr_bwd2_kernel<1, B200SP_ACT_RELU6>, grid, dim3(RNT), smem, st, *dy, w9c, (float*)g_in, dw9c, b, gm);
             else    b200sp_launch_pdl(dwr_bwd2_kernel<1, B200SP_ACT_RELU>, grid, dim3(RNT), smem, st, *dy, w9c, (float*)g_in, dw9c, b, gm);
+        } else if (dw_prefetch() == 2) {
+            if (r6) b200sp_launch_pdl(dwr_bwd2_kernel<2, B200SP_ACT_RELU6, true>, grid, dim3(RNT), smem, st, *dy, w9c, (float*)g_in, dw9c, b, gm);
+            else    b200sp_launch_pdl(dwr_bwd2_kernel<2, B200SP_ACT_RELU, true>, grid, dim3(RNT), smem, st, *dy, w9c, (float*)g_in, dw9c, b, gm);
         } else {
             if (r6) b200sp_launch_pdl(dwr_bwd2_kernel<2, B200SP_ACT_RELU6>, grid, dim3(RNT), smem, st, *dy, w9c, (float*)g_in, dw9c, b, gm);
             else    b200sp_launch_pdl(dwr_bwd2_kernel<2, B200SP_ACT_RELU>, grid, dim3(RNT), smem, st, *dy, w9c, (float*)g_in, dw9c, b, gm);

@@ -1035,7 +1035,7 @@ template <int EPI>
 int launch_pre(Tcg2Args& a, const float* A, int lda, size_t planeA, const float* B, int ldb, size_t planeB, cudaStream_t st) {
     using E = ETf;
     constexpr int EPI_W = 8, EPI_SETS = 2;
-    auto kern = tcgemm2_kernel<TCG_LAY_KM, TCG_LAY_KM, EPI, XM_PLAIN, XM_PLAIN, false, true, 8>;
+    auto kern = tcgemm2_kernel<TCG_LAY_KM, TCG_LAY_KM, EPI, XM_PLAIN, XM_PLAIN, false, true, 8, 8>;       // launch bound 576 threads (320 launched): 112 registers
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
