@@ -48,7 +48,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index, self.rows, self._halt = index, [], threading.Event()
-        self.nvml = None
+        self.nvml, self._mx = None, None
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -61,13 +61,14 @@ class ClockSampler(threading.Thread):
             self.source = 'nvidia-smi'
 
     def _sample_nvml(self):
+        # two driver queries per sample (current SM clock, event reasons): every NVML call takes a driver lock that kernel / graph
+        # launches also need -- with the maximum clock and the power draw queried each time the host-driven end-to-end loop ran
+        # 6 % behind the device-resident one (tools/e2e_probe.py without a sampler: 0.4 %)
         n = self.nvml
         sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
-        mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
-        try:
-            pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
-        except Exception:
-            pw = 0.0
+        if self._mx is None:
+            self._mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+        mx, pw = self._mx, 0.0
         get = getattr(n, 'nvmlDeviceGetCurrentClocksEventReasons', None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
         r = int(get(self.h))
         bit = lambda name, alt: getattr(n, name, getattr(n, alt, 0))
@@ -90,7 +91,7 @@ class ClockSampler(threading.Thread):
                         self.rows.append(f)
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.25)
 
     def stop(self):
         self._halt.set()
