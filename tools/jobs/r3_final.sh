@@ -1,0 +1,13 @@
+#!/bin/bash
+# round-2 closing evidence (1 GPU): GPU test suite, smoke, bench (both arms), DANN bench, step profile, ncu launch list
+O=gpurun_out/r3_final; mkdir -p $O
+export B200SP_NO_AUTOBUILD=1
+timeout 1500 python -m pytest -q tests -m gpu 2>&1 | tail -15 > $O/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1
+timeout 1500 python bench.py --profile-out $O/step_profile.txt > $O/bench.json 2> $O/bench.err
+timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > $O/bench_reference.json 2> $O/bench_reference.err
+timeout 600 python bench.py --workload dann --steps 50 --warmup 5 --no-cpu-baseline > $O/bench_dann.json 2> $O/bench_dann.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $O/launches.csv python bench.py --steps 2 --warmup 3 --no-secondary --no-cpu-baseline > $O/ncu_bench.log 2>&1
+timeout 300 python tools/spn_bench.py > $O/spn_profile.txt 2>&1
+timeout 300 python tools/styleaug_bench.py > $O/styleaug_profile.txt 2>&1
+tail -3 $O/pytest_gpu.log; tail -2 $O/smoke.log; head -c 600 $O/bench.json
