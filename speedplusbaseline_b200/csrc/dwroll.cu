@@ -777,9 +777,9 @@ int roll_geom(RGeom& gm, dim3& grid, int B, int H, int W, int C, int stride, int
     const long long base = (long long)B * ncolgroups * C4;
     const long long target = (long long)NUM_SMS * 3072;
     int nseg = (int)((target + base - 1) / base);
-    static int small_seg = -1;
-    if (small_seg < 0) { const char* e = getenv("B200SP_DW_SMALLSEG"); small_seg = (e && e[0] == '1') ? 1 : 0; }
-    const int maxseg = rows >= 32 ? rows / 8 : (small_seg ? (rows >= 3 ? rows / 3 : 1) : (rows >= 16 ? rows / 8 : 1));
+    static int small_seg = -1;       // B200SP_DW_SMALLSEG=<n>: maps below 32 rows are cut into segments of >= n rows (0: off)
+    if (small_seg < 0) { const char* e = getenv("B200SP_DW_SMALLSEG"); small_seg = e ? atoi(e) : 0; if (small_seg < 0) small_seg = 0; }
+    const int maxseg = rows >= 32 ? rows / 8 : (small_seg ? (rows >= small_seg ? rows / small_seg : 1) : (rows >= 16 ? rows / 8 : 1));
     if (nseg > maxseg) nseg = maxseg;
     if (nseg < 1) nseg = 1;
     gm.SEG = (rows + nseg - 1) / nseg;

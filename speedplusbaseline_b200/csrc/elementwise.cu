@@ -13,6 +13,40 @@ __global__ void __launch_bounds__(EW_NT) bn_apply_kernel(const T* __restrict__ y
                                                          int act, T* __restrict__ out, long long n4, int C4) {
     pdl_trigger();
     pdl_wait();
+    // four independent 16-byte pieces per thread and iteration (all loads issued before any arithmetic), 32-bit index arithmetic:
+    // one piece per iteration with a 64-bit modulo ran at 1.8 TB/s
+    if (n4 < (1ll << 30)) {
+        const unsigned stride = gridDim.x * EW_NT, n = (unsigned)n4, uc4 = (unsigned)C4;
+        unsigned i = blockIdx.x * EW_NT + threadIdx.x;
+        for (; i + 3 * stride < n; i += 4 * stride) {
+            float4 v[4], r[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = Vec4<T>::ld(y + (size_t)(i + u * stride) * 4);
+            if (res) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) r[u] = Vec4<T>::ld(res + (size_t)(i + u * stride) * 4);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = (int)((i + u * stride) % uc4) * 4;
+                const float4 a = ldg4(scale + c), b = ldg4(shift + c);
+                float4 o = make_float4(act_fwd(fmaf(v[u].x, a.x, b.x), act), act_fwd(fmaf(v[u].y, a.y, b.y), act),
+                                       act_fwd(fmaf(v[u].z, a.z, b.z), act), act_fwd(fmaf(v[u].w, a.w, b.w), act));
+                if (res) { o.x += r[u].x; o.y += r[u].y; o.z += r[u].z; o.w += r[u].w; }
+                Vec4<T>::st(out + (size_t)(i + u * stride) * 4, o);
+            }
+        }
+        for (; i < n; i += stride) {
+            const int c = (int)(i % uc4) * 4;
+            float4 v = Vec4<T>::ld(y + (size_t)i * 4);
+            const float4 a = ldg4(scale + c), b = ldg4(shift + c);
+            v = make_float4(act_fwd(fmaf(v.x, a.x, b.x), act), act_fwd(fmaf(v.y, a.y, b.y), act),
+                            act_fwd(fmaf(v.z, a.z, b.z), act), act_fwd(fmaf(v.w, a.w, b.w), act));
+            if (res) { const float4 rr = Vec4<T>::ld(res + (size_t)i * 4); v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
+            Vec4<T>::st(out + (size_t)i * 4, v);
+        }
+        return;
+    }
     for (long long i = (long long)blockIdx.x * EW_NT + threadIdx.x; i < n4; i += (long long)gridDim.x * EW_NT) {
         const int c = (int)(i % C4) * 4;
         float4 v = Vec4<T>::ld(y + i * 4);
@@ -350,7 +384,7 @@ extern "C" int b200sp_bn_apply(const void* y, const float* scale, const float* s
     if (C % 4) return B200SP_EINVAL;
     const long long n4 = M * (C / 4);
     if (dtype == B200SP_F32)
-        b200sp_launch_pdl(bn_apply_kernel<float>, dim3(ew_grid(n4)), dim3(EW_NT), 0, (cudaStream_t)stream, (const float*)y, scale, shift,
+        b200sp_launch_pdl(bn_apply_kernel<float>, dim3(ew_grid((n4 + 3) / 4)), dim3(EW_NT), 0, (cudaStream_t)stream, (const float*)y, scale, shift,
                           (const float*)residual, act, (float*)out, n4, C / 4);
     else
         bn_apply_kernel<bf16><<<ew_grid(n4), EW_NT, 0, (cudaStream_t)stream>>>((const bf16*)y, scale, shift, (const bf16*)residual,

@@ -154,6 +154,10 @@ def _summarise(best, reps):
     top = sorted(best, key=lambda r: -r[2])[:25]
     for n, b, t, tag in top:
         lines.append('%-24s %10.1f us %10.2f MB %9.1f GB/s   [%s]' % (n, t, b / 1e6, b / 1e3 / max(t, 1e-3), tag))
+    lines.append('')
+    lines.append('# every launch in issue order')
+    for n, b, t, tag in best:
+        lines.append('%-24s %10.1f us %10.2f MB %9.1f GB/s   [%s]' % (n, t, b / 1e6, b / 1e3 / max(t, 1e-3), tag))
     n, b, t, tag = top[0]
     hbm = 6545.9
     p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'MEASURED_PEAKS.json')
