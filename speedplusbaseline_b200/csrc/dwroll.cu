@@ -773,7 +773,10 @@ int roll_geom(RGeom& gm, dim3& grid, int B, int H, int W, int C, int stride, int
     gm.nWG = ncolgroups;
     // split the rolled dimension until ~12 warps/SM x 2 waves of threads exist (segments of >= 8 rows: halo overhead <= 25 %).
     // Finer segments for the small maps (B200SP_DW_SMALLSEG=1: >= 3 rows, 3-4x more CTAs) were measured and are SLOWER
-    // (dw_bwd 1214 -> 1323 us per step, job r2v): those launches are bound by their per-CTA reductions, not by parallelism.
+    // (dw_bwd 1214 -> 1323 us per step, job r2v; whole step 5.40 -> 5.49 / 5.81 / 6.37 ms with segments of >= 4 / 2 / 1 rows, job r3u):
+    // those launches are bound by their per-CTA reductions (same-address atomics), not by parallelism.  Whole-image "slab" kernels
+    // for the 7x7 / 14x14 maps (all loads issued at once into shared memory, one CTA per 1-4 images and 64 channels) were written
+    // and measured too: 5.43 vs 5.40 ms in-graph -- no gain, not kept (job r3v).
     const long long base = (long long)B * ncolgroups * C4;
     const long long target = (long long)NUM_SMS * 3072;
     int nseg = (int)((target + base - 1) / base);

@@ -158,7 +158,10 @@ def test_pw_wgrad_streaming_reduction(M, N, K, dy_mode, x_mode):
     assert rel(dw + 0.25, ref) < 2e-5
 
 
-@pytest.mark.parametrize('B,H,W,Cc,s', [(2, 13, 9, 32, 1), (3, 14, 14, 144, 2), (2, 7, 7, 1280, 1), (1, 33, 20, 96, 2), (2, 56, 56, 24, 1)])
+@pytest.mark.parametrize('B,H,W,Cc,s', [(2, 13, 9, 32, 1), (3, 14, 14, 144, 2), (2, 7, 7, 1280, 1), (1, 33, 20, 96, 2), (2, 56, 56, 24, 1),
+                                        # small maps with C % 64 == 0: the slab kernels (whole images in shared memory)
+                                        (3, 14, 14, 576, 1), (3, 14, 14, 576, 2), (11, 7, 7, 960, 1), (2, 14, 14, 384, 1), (9, 7, 7, 64, 2),
+                                        (48, 7, 7, 320, 1), (5, 13, 11, 128, 2), (1, 2, 3, 64, 1)])
 def test_dw_fwd(B, H, W, Cc, s):
     g = _g(H * W + Cc + s)
     x = torch.randn(B, H, W, Cc, generator=g)
@@ -179,7 +182,9 @@ def test_dw_fwd(B, H, W, Cc, s):
     assert rel(bn.rstd, 1 / torch.sqrt(ref.var((0, 1, 2), unbiased=False) + 1e-5)) < 1e-5
 
 
-@pytest.mark.parametrize('B,H,W,Cc,s', [(2, 13, 9, 32, 1), (3, 14, 14, 144, 2), (2, 7, 7, 320, 1), (1, 33, 20, 96, 2), (2, 28, 28, 192, 1)])
+@pytest.mark.parametrize('B,H,W,Cc,s', [(2, 13, 9, 32, 1), (3, 14, 14, 144, 2), (2, 7, 7, 320, 1), (1, 33, 20, 96, 2), (2, 28, 28, 192, 1),
+                                        (3, 14, 14, 576, 1), (3, 14, 14, 576, 2), (11, 7, 7, 960, 1), (2, 14, 14, 384, 1), (9, 7, 7, 64, 2),
+                                        (5, 13, 11, 128, 2), (1, 2, 3, 64, 1)])
 @pytest.mark.parametrize('with_skip', [False, True])
 def test_dw_bwd_fused(B, H, W, Cc, s, with_skip):
     g = _g(H + W + Cc + s)
