@@ -157,6 +157,82 @@ __device__ __forceinline__ void bn_bwd_finalize_channel(const b200sp_bnbwd& bn, 
     bn.s2[c] = 0.0;
 }
 
+// All channels by the threads of one CTA.  Four channels per thread at a time with EVERY load of the batch issued before the first
+// store: the per-channel form above costs ~4 dependent L2 round trips per channel (the stores may alias the later loads, so the
+// compiler cannot hoist them), which made the last CTA's 10 iterations over 1280 channels a 20-25 us serial tail of every
+// small-map depthwise launch (19 ns per channel in the r3t per-launch profile).
+__device__ __forceinline__ void bn_fwd_finalize_all(const b200sp_bnfwd& bn, int C, double count, int tid, int nthreads) {
+    constexpr int NB = 4;
+    for (int c0 = tid; c0 < C; c0 += nthreads * NB) {
+        double s[NB], q[NB];
+        float ga[NB], be[NB], rm[NB], rv[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            const int c = c0 + j * nthreads;
+            const bool ok = c < C;
+            s[j] = ok ? ld_cg_f64(bn.sum + c) : 0.0;
+            q[j] = ok ? ld_cg_f64(bn.sumsq + c) : 0.0;
+            ga[j] = ok ? bn.gamma[c] : 0.f;
+            be[j] = ok ? bn.beta[c] : 0.f;
+            rm[j] = (ok && bn.running_mean) ? bn.running_mean[c] : 0.f;
+            rv[j] = (ok && bn.running_mean) ? bn.running_var[c] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            const int c = c0 + j * nthreads;
+            if (c >= C) continue;
+            const double mean = s[j] / count;
+            double var = q[j] / count - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const double rstd = 1.0 / sqrt(var + (double)bn.eps);
+            bn.scale[c] = (float)((double)ga[j] * rstd);
+            bn.shift[c] = (float)((double)be[j] - mean * (double)ga[j] * rstd);
+            bn.mean[c] = (float)mean;
+            bn.rstd[c] = (float)rstd;
+            if (bn.running_mean) {
+                const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+                bn.running_mean[c] = (float)((1.0 - bn.momentum) * (double)rm[j] + bn.momentum * mean);
+                bn.running_var[c] = (float)((1.0 - bn.momentum) * (double)rv[j] + bn.momentum * unb);
+            }
+            bn.sum[c] = 0.0;
+            bn.sumsq[c] = 0.0;
+        }
+    }
+}
+__device__ __forceinline__ void bn_bwd_finalize_all(const b200sp_bnbwd& bn, int C, double count, int tid, int nthreads) {
+    constexpr int NB = 4;
+    for (int c0 = tid; c0 < C; c0 += nthreads * NB) {
+        double s1[NB], s2[NB];
+        float sc[NB], rs[NB], mu[NB], dg[NB], db[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            const int c = c0 + j * nthreads;
+            const bool ok = c < C;
+            s1[j] = ok ? ld_cg_f64(bn.s1 + c) : 0.0;
+            s2[j] = ok ? ld_cg_f64(bn.s2 + c) : 0.0;
+            sc[j] = ok ? bn.scale[c] : 0.f;
+            rs[j] = ok ? bn.rstd[c] : 0.f;
+            mu[j] = ok ? bn.mean[c] : 0.f;
+            dg[j] = ok ? bn.dgamma[c] : 0.f;
+            db[j] = ok ? bn.dbeta[c] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            const int c = c0 + j * nthreads;
+            if (c >= C) continue;
+            const double scd = sc[j], rstd = rs[j], mean = mu[j];
+            const double cB = -scd * rstd * s2[j] / count;
+            bn.cA[c] = (float)scd;
+            bn.cB[c] = (float)cB;
+            bn.cC[c] = (float)(-scd * s1[j] / count - cB * mean);
+            bn.dgamma[c] = dg[j] + (float)s2[j];
+            bn.dbeta[c] = db[j] + (float)s1[j];
+            bn.s1[c] = 0.0;
+            bn.s2[c] = 0.0;
+        }
+    }
+}
+
 // Elect the last CTA of the grid.  Call after this CTA's global atomics.  Returns true in every
 // thread of the last CTA (after which it may read the accumulators with ld.cg).
 __device__ __forceinline__ bool grid_last_cta(uint32_t* ticket, uint32_t total) {

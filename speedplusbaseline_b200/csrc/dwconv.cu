@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(DW_NT, 2) dw_fwd_kernel(const b200sp_vtensor x
         atomicAdd(bn.sumsq + cbase + tid, (double)s_sq[tid]);
     }
     if (grid_last_cta(bn.ticket, gridDim.x * gridDim.y))
-        for (int cc = tid; cc < gm.C; cc += DW_NT) bn_fwd_finalize_channel(bn, cc, gm.count);
+        bn_fwd_finalize_all(bn, gm.C, gm.count, tid, DW_NT);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(DW_NT, 1) dw_bwd_kernel(const b200sp_vtensor d
         }
     }
     if (cx.do_stats && grid_last_cta(bn.ticket, gridDim.x * gridDim.y))
-        for (int cc = tid; cc < gm.C; cc += DW_NT) bn_bwd_finalize_channel(bn, cc, gm.count);
+        bn_bwd_finalize_all(bn, gm.C, gm.count, tid, DW_NT);
 }
 
 int dw_geom(DwGeom& gm, dim3& grid, int B, int H, int W, int C, int stride, bool over_input) {

@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(RNT, 3) dwr_fwd_kernel(const b200sp_vtensor x,
         atomicAdd(bn.sumsq + cbase + tid, (double)s_sq[tid]);
     }
     if (grid_last_cta(bn.ticket, gridDim.x * gridDim.y))
-        for (int cc = tid; cc < gm.C; cc += RNT) bn_fwd_finalize_channel(bn, cc, gm.count);
+        bn_fwd_finalize_all(bn, gm.C, gm.count, tid, RNT);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(RNT, 3) dwr_bwd_kernel(const b200sp_vtensor dy
         }
     }
     if (cx.do_stats && grid_last_cta(bn.ticket, gridDim.x * gridDim.y))
-        for (int cc = tid; cc < gm.C; cc += RNT) bn_bwd_finalize_channel(bn, cc, gm.count);
+        bn_bwd_finalize_all(bn, gm.C, gm.count, tid, RNT);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -639,7 +639,7 @@ __global__ void __launch_bounds__(RNT, PF ? (S == 2 ? 3 : 2) : (S == 2 ? 4 : DWR
         atomicAdd(bn.s2 + cbase + tid, (double)b);
     }
     if (grid_last_cta(bn.ticket, gridDim.x * gridDim.y))
-        for (int cc = tid; cc < gm.C; cc += RNT) bn_bwd_finalize_channel(bn, cc, gm.count);
+        bn_bwd_finalize_all(bn, gm.C, gm.count, tid, RNT);
 }
 
 // Forward, second generation (same recipe as dwr_bwd2_kernel; B200SP_DW=2).  Input = act(BN(y_prev)) with the activation fixed
@@ -758,7 +758,7 @@ __global__ void __launch_bounds__(RNT, PF ? (S == 2 ? 3 : 2) : (S == 2 ? 4 : DWR
         atomicAdd(bn.sumsq + cbase + tid, (double)b);
     }
     if (grid_last_cta(bn.ticket, gridDim.x * gridDim.y))
-        for (int cc = tid; cc < gm.C; cc += RNT) bn_fwd_finalize_channel(bn, cc, gm.count);
+        bn_fwd_finalize_all(bn, gm.C, gm.count, tid, RNT);
 }
 
 // rows: number of rolled rows; cols: number of column groups; count: BatchNorm population

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(EW_NT) bn_bwd_reduce_kernel(const T* __restric
         atomicAdd(bn.s2 + c, (double)s2s[0][cl] + (double)s2s[1][cl] + (double)s2s[2][cl] + (double)s2s[3][cl]);
     }
     if (grid_last_cta(bn.ticket, gridDim.x * gridDim.y))
-        for (int cc = threadIdx.x; cc < C; cc += EW_NT) bn_bwd_finalize_channel(bn, cc, (double)M);
+        bn_bwd_finalize_all(bn, C, (double)M, threadIdx.x, EW_NT);
 }
 
 // column sums of a virtual [M,N] tensor (bias gradients): out[n] += sum_m dy[m,n]

@@ -737,10 +737,8 @@ __global__ void __launch_bounds__(NT, 1) tcgemm_kernel(const TcgArgs g) {
             epi_bar();
             if (*s_flag) {
                 __threadfence();
-                for (int c = tid; c < g.Q; c += EPI_T) {
-                    if (EPI == TCG_EPI_FWD) bn_fwd_finalize_channel(g.bnf, c, g.count);
-                    else                    bn_bwd_finalize_channel(g.bnb, c, g.count);
-                }
+                if (EPI == TCG_EPI_FWD) bn_fwd_finalize_all(g.bnf, g.Q, g.count, tid, EPI_T);
+                else                    bn_bwd_finalize_all(g.bnb, g.Q, g.count, tid, EPI_T);
             }
         }
     }

@@ -126,6 +126,10 @@ def _profile_reps(stepper, images, target, reps):
     best = None
     for _ in range(reps):
         with LaunchTimer() as lt:
+            # keep the GPU busy for ~8 ms first: the host then runs ahead and every (event, launch, event) triple of the step is
+            # already queued when the GPU reaches it -- the intervals are kernel time, not kernel time + host launch latency
+            # (small kernels read 5-10 us too long otherwise)
+            torch.cuda._sleep(16_000_000)
             stepper.eager(images, target)
         rows = lt.rows()
         if best is None:
@@ -143,7 +147,7 @@ def _summarise(best, reps):
         agg[n][2] += b
     total = sum(v[1] for v in agg.values())
     step_bytes = sum(v[2] for v in agg.values())
-    lines = ['# per-kernel-family totals for ONE eager KRN train step (CUDA events, min of %d reps)' % reps,
+    lines = ['# per-kernel-family totals for ONE eager KRN train step (CUDA events around every launch, launches queued ahead of the GPU, min of %d reps)' % reps,
              '%-24s %6s %10s %7s %12s %9s' % ('kernel', 'calls', 'us', 'share', 'alg_MB', 'GB/s')]
     fam = sorted(agg.items(), key=lambda kv: -kv[1][1])
     for n, (c, t, b) in fam:
