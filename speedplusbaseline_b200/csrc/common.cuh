@@ -161,8 +161,11 @@ __device__ __forceinline__ void bn_bwd_finalize_channel(const b200sp_bnbwd& bn, 
 // store: the per-channel form above costs ~4 dependent L2 round trips per channel (the stores may alias the later loads, so the
 // compiler cannot hoist them), which made the last CTA's 10 iterations over 1280 channels a 20-25 us serial tail of every
 // small-map depthwise launch (19 ns per channel in the r3t per-launch profile).
+#ifndef BN_FIN_NB
+#define BN_FIN_NB 4          // measured on the whole step: 2 -> see profiles/r2_step_switches.txt, 4 -> 5.11 ms, 8 -> 5.25 ms (register pressure where it is inlined)
+#endif
 __device__ __forceinline__ void bn_fwd_finalize_all(const b200sp_bnfwd& bn, int C, double count, int tid, int nthreads) {
-    constexpr int NB = 4;
+    constexpr int NB = BN_FIN_NB;
     for (int c0 = tid; c0 < C; c0 += nthreads * NB) {
         double s[NB], q[NB];
         float ga[NB], be[NB], rm[NB], rv[NB];
@@ -200,7 +203,7 @@ __device__ __forceinline__ void bn_fwd_finalize_all(const b200sp_bnfwd& bn, int 
     }
 }
 __device__ __forceinline__ void bn_bwd_finalize_all(const b200sp_bnbwd& bn, int C, double count, int tid, int nthreads) {
-    constexpr int NB = 4;
+    constexpr int NB = BN_FIN_NB;
     for (int c0 = tid; c0 < C; c0 += nthreads * NB) {
         double s1[NB], s2[NB];
         float sc[NB], rs[NB], mu[NB], dg[NB], db[NB];
