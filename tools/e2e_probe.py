@@ -66,6 +66,29 @@ def e():      # graph replay only (static inputs already in place)
             st._graphs[1].replay()
 
 
+# pure H2D bandwidth of the pinned batch
+torch.cuda.synchronize()
+buf = torch.empty_like(d_img)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(20):
+    buf.copy_(h_img, non_blocking=True)
+e1.record()
+torch.cuda.synchronize()
+print('H2D of the pinned 28.9 MB batch: %.3f ms (%.1f GB/s)' % (e0.elapsed_time(e1) / 20, 28.9e-3 / (e0.elapsed_time(e1) / 20 / 1e3)), flush=True)
+
+sampler = None
+if len(sys.argv) > 2 and sys.argv[2] == 'sampler':
+    sys.path.insert(0, ROOT)
+    import bench
+    sampler = bench.ClockSampler(0)
+    sampler.start()
+    print('clock sampler running', flush=True)
+
 for name, fn in (('device batch', a), ('prefetcher, host batch (H2D)', b), ('prefetcher, host batch + loss D2H', c),
                  ('prefetcher, device batch (no PCIe)', d), ('graph replays only', e), ('device batch again', a)):
     timed(name, fn)
+for name, fn in (('prefetcher, host batch + loss D2H (2)', c), ('device batch (2)', a), ('prefetcher, host batch + loss D2H (3)', c)):
+    timed(name, fn)
+if sampler:
+    print(sampler.stop())
