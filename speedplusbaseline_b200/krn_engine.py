@@ -98,6 +98,10 @@ class _Ctx:
         return self.sums.data_ptr() + 8 * (row * st.totC + st.bn_off[bn_i])
 
 
+import os as _os
+_POISON = _os.environ.get('B200SP_DEBUG_POISON') == '1'
+
+
 class KRNEngine:
     def __init__(self, num_keypoints=11, prefix='', dann=False, device=None, dtype=L.F32, tf32_gemm=False):
         """tf32_gemm: the `--use_fp16` mode -- fp32 storage everywhere, 1x1-convolution GEMMs in SINGLE-pass TF32 (fp16's 10-bit
@@ -131,6 +135,8 @@ class KRNEngine:
         t = d.get(name)
         if t is None or tuple(t.shape) != tuple(shape):
             t = torch.empty(shape, dtype=self.tdtype, device=self.device)
+            if _POISON:          # B200SP_DEBUG_POISON=1: a kernel that reads a buffer before its producer wrote it shows up as NaN
+                t.fill_(float('nan'))
             d[name] = t
         return t
 
