@@ -98,6 +98,11 @@ __device__ __forceinline__ void job_trans(const OpSplitJob& j, int blk, float* s
 
 __global__ void __launch_bounds__(OS_NT) opsplit_kernel(const __grid_constant__ OpSplitJob j0, const __grid_constant__ OpSplitJob j1, int blocks0) {
     __shared__ __align__(16) float s[TR_C * TR_LD];
+    // programmatic dependent launch: this grid may be scheduled while its predecessor drains, but it overwrites the workspace the
+    // previous GEMM may still be reading -- nothing is touched before griddepcontrol.wait (= predecessor complete and flushed);
+    // the trigger right after lets the GEMM that consumes these planes set up (barriers, TMEM) while this kernel runs
+    pdl_wait();
+    pdl_trigger();
     const bool first = (int)blockIdx.x < blocks0;
     const OpSplitJob& j = first ? j0 : j1;
     const int blk = first ? blockIdx.x : blockIdx.x - blocks0;
@@ -112,11 +117,10 @@ inline int job_blocks(const OpSplitJob& j) {
 
 }  // namespace
 
-// both operands of one GEMM in one launch.  A plain launch (no programmatic-dependent-launch attribute): the previous GEMM may
-// still be reading the workspace these jobs overwrite, so this kernel must not start before that grid has completed.
+// both operands of one GEMM in one launch
 int opsplit_launch(const OpSplitJob& a, const OpSplitJob& b, cudaStream_t st) {
     const int b0 = job_blocks(a), b1 = job_blocks(b);
-    opsplit_kernel<<<b0 + b1, OS_NT, 0, st>>>(a, b, b0);
+    { cudaError_t le = b200sp_launch_pdl(opsplit_kernel, dim3(b0 + b1), dim3(OS_NT), 0, st, a, b, b0); if (le != cudaSuccess) return (int)le; }
     B200SP_COUNT_LAUNCH();
     B200SP_RETURN_LAST();
 }

@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(WG_NT, 2) wgdirect_kernel(const WgArgs a) {
     float* s_par = ws + WG_ST * stage_f;                          // cA cB cC [N] | sc sh [K]
     const int tid = threadIdx.x;
     pdl_wait();
+    pdl_trigger();
     if (AMODE == WG_XF) for (int i = tid; i < N; i += WG_NT) { s_par[i] = __ldg(a.cA + i); s_par[N + i] = __ldg(a.cB + i); s_par[2 * N + i] = __ldg(a.cC + i); }
     if (BMODE == WG_XF) for (int i = tid; i < K; i += WG_NT) { s_par[3 * N + i] = __ldg(a.sc + i); s_par[3 * N + K + i] = __ldg(a.sh + i); }
     const ActP act = act_params(a.act);
@@ -202,7 +203,7 @@ int wg_launch(WgArgs& a, size_t smem, int grid, cudaStream_t st) {
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    wgdirect_kernel<AMODE, BMODE><<<grid, WG_NT, smem, st>>>(a);
+    { cudaError_t le = b200sp_launch_pdl(wgdirect_kernel<AMODE, BMODE>, dim3(grid), dim3(WG_NT), smem, st, a); if (le != cudaSuccess) return (int)le; }
     B200SP_COUNT_LAUNCH();
     B200SP_RETURN_LAST();
 }
