@@ -353,6 +353,8 @@ constexpr int STEM_C = 32;
 template <typename T>
 __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, T* __restrict__ y,
                                                        const b200sp_bnfwd bn, const int has_bn, int B, int H, int W, int Ho, int Wo) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float s_w[27][STEM_C];            // [tap][cout]
     __shared__ float s_t[256][STEM_C + 1];       // staged outputs for the column sums
     __shared__ float s_acc[2][8][STEM_C];
@@ -472,6 +474,8 @@ constexpr int SW_XP = 232;                      // padded row pitch of the stage
 template <typename T>
 __global__ void __launch_bounds__(256) stem_wgrad2_kernel(const float* __restrict__ x, const b200sp_vtensor dy, float* __restrict__ dw,
                                                           int B, int H, int W, int Ho, int Wo) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ __align__(16) float sw_smem[];
     float* s_x = sw_smem;                        // [3 ci][3 kh][SW_XP]
     float* s_dy = sw_smem + 9 * SW_XP;           // [Wo][32]
@@ -582,7 +586,7 @@ extern "C" int b200sp_stem_fwd(const float* x_nchw, const float* w, void* y, con
     if (grid > NUM_SMS * 4) grid = NUM_SMS * 4;
     b200sp_bnfwd b = {};
     if (bn) b = *bn;
-    if (dtype == B200SP_F32) stem_fwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, w, (float*)y, b, bn != nullptr, B, H, W, Ho, Wo);
+    if (dtype == B200SP_F32) b200sp_launch_pdl(stem_fwd_kernel<float>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, x_nchw, w, (float*)y, b, (int)(bn != nullptr), B, H, W, Ho, Wo);
     else stem_fwd_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, w, (bf16*)y, b, bn != nullptr, B, H, W, Ho, Wo);
     B200SP_COUNT_LAUNCH();
     B200SP_RETURN_LAST();
@@ -600,7 +604,7 @@ extern "C" int b200sp_stem_wgrad(const float* x_nchw, const b200sp_vtensor* dy, 
     if (v2 && dtype == B200SP_F32 && W % 4 == 0 && W + 1 <= SW_XP && Wo * STEM_C >= 4 * 896 && ((uintptr_t)x_nchw & 15) == 0) {
         const size_t smem = sizeof(float) * (9 * SW_XP + (size_t)Wo * STEM_C);
         int g2 = B * Ho < NUM_SMS * 4 ? B * Ho : NUM_SMS * 4;
-        stem_wgrad2_kernel<float><<<g2, 256, smem, (cudaStream_t)stream>>>(x_nchw, *dy, dw, B, H, W, Ho, Wo);
+        b200sp_launch_pdl(stem_wgrad2_kernel<float>, dim3(g2), dim3(256), smem, (cudaStream_t)stream, x_nchw, *dy, dw, B, H, W, Ho, Wo);
         B200SP_COUNT_LAUNCH();
         B200SP_RETURN_LAST();
     }

@@ -133,6 +133,8 @@ __global__ void add_i64_kernel(int64_t* p, long long n, long long v) {
 template <typename T>
 __global__ void __launch_bounds__(EW_NT) reorg_cat_fwd_kernel(const b200sp_vtensor xr, const b200sp_vtensor x1, T* __restrict__ out,
                                                               int B, int h, int w, int Cr, int C1) {
+    pdl_wait();
+    pdl_trigger();
     const int Ct = 4 * Cr + C1, Ct4 = Ct / 4;
     const long long n4 = (long long)B * h * w * Ct4;
     for (long long i = (long long)blockIdx.x * EW_NT + threadIdx.x; i < n4; i += (long long)gridDim.x * EW_NT) {
@@ -157,6 +159,8 @@ template <typename T>
 __global__ void __launch_bounds__(EW_NT) reorg_cat_bwd_kernel(const T* __restrict__ dcat, T* __restrict__ g_r, T* __restrict__ g_1,
                                                               const b200sp_bnbwd bn_r, const b200sp_bnbwd bn_1,
                                                               int B, int h, int w, int Cr, int C1) {
+    pdl_wait();
+    pdl_trigger();
     const int Ct = 4 * Cr + C1, Ct4 = Ct / 4;
     const long long n4 = (long long)B * h * w * Ct4;
     for (long long i = (long long)blockIdx.x * EW_NT + threadIdx.x; i < n4; i += (long long)gridDim.x * EW_NT) {
@@ -196,6 +200,8 @@ constexpr int HF_KC = 128, HF_LD = HF_KC + 4, HF_MAXB = 64;
 template <typename T>
 __global__ void __launch_bounds__(EW_NT) head_fwd2_kernel(const b200sp_vtensor x, const float* __restrict__ w, float* __restrict__ logits,
                                                           int B, int HWC, int C, int N) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ __align__(16) float hf_smem[];
     float* s_x = hf_smem;                       // [B][HF_LD]
     float* s_w = hf_smem + (size_t)B * HF_LD;   // [N][HF_LD]
@@ -284,6 +290,8 @@ __global__ void __launch_bounds__(EW_NT) head_fwd_kernel(const b200sp_vtensor x,
 }
 
 __global__ void head_bias_kernel(const float* __restrict__ bias, float* __restrict__ logits, int B, int N) {
+    pdl_wait();
+    pdl_trigger();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < B * N) logits[i] = bias[i % N];
 }
@@ -292,6 +300,8 @@ __global__ void head_bias_kernel(const float* __restrict__ bias, float* __restri
 __global__ void krn_loss_kernel(const float* __restrict__ logits, const float* __restrict__ target, float* __restrict__ loss3,
                                 float* __restrict__ dlogits, float* __restrict__ dbias, const float* __restrict__ loss_scale,
                                 int B, int N) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float s_lx[EW_NT], s_ly[EW_NT];
     const int tid = threadIdx.x, nk = N / 2;
     const float ls = loss_scale ? loss_scale[0] : 1.f;
@@ -325,6 +335,8 @@ __global__ void __launch_bounds__(EW_NT) head_bwd_kernel(const float* __restrict
                                                          const float* __restrict__ w, T* __restrict__ g, float* __restrict__ dw,
                                                          float* __restrict__ dbias, const b200sp_bnbwd bn, const int has_bn,
                                                          int B, int HWC, int C, int N) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ float s_dl[];     // [B][HEAD_MAXN]
     const int tid = threadIdx.x;
     for (int i = tid; i < B * HEAD_MAXN; i += EW_NT) {
@@ -446,7 +458,7 @@ extern "C" int b200sp_reorg_cat_fwd(const b200sp_vtensor* xr, const b200sp_vtens
     if (dtype != B200SP_F32 && dtype != B200SP_BF16) return B200SP_ENOSYS;
     if (Cr % 4 || C1 % 4) return B200SP_EINVAL;
     const long long n4 = (long long)B * h * w * ((4 * Cr + C1) / 4);
-    if (dtype == B200SP_F32) reorg_cat_fwd_kernel<float><<<ew_grid(n4), EW_NT, 0, (cudaStream_t)stream>>>(*xr, *x1, (float*)out, B, h, w, Cr, C1);
+    if (dtype == B200SP_F32) b200sp_launch_pdl(reorg_cat_fwd_kernel<float>, dim3(ew_grid(n4)), dim3(EW_NT), 0, (cudaStream_t)stream, *xr, *x1, (float*)out, B, h, w, Cr, C1);
     else reorg_cat_fwd_kernel<bf16><<<ew_grid(n4), EW_NT, 0, (cudaStream_t)stream>>>(*xr, *x1, (bf16*)out, B, h, w, Cr, C1);
     B200SP_COUNT_LAUNCH();
     B200SP_RETURN_LAST();
@@ -458,8 +470,8 @@ extern "C" int b200sp_reorg_cat_bwd(const void* dcat, void* g_r, void* g_1, cons
     if (Cr % 4 || C1 % 4) return B200SP_EINVAL;
     const long long n4 = (long long)B * h * w * ((4 * Cr + C1) / 4);
     if (dtype == B200SP_F32)
-        reorg_cat_bwd_kernel<float><<<ew_grid(n4), EW_NT, 0, (cudaStream_t)stream>>>((const float*)dcat, (float*)g_r, (float*)g_1,
-                                                                                   *bn_r, *bn_1, B, h, w, Cr, C1);
+        b200sp_launch_pdl(reorg_cat_bwd_kernel<float>, dim3(ew_grid(n4)), dim3(EW_NT), 0, (cudaStream_t)stream, (const float*)dcat, (float*)g_r, (float*)g_1,
+                          *bn_r, *bn_1, B, h, w, Cr, C1);
     else
         reorg_cat_bwd_kernel<bf16><<<ew_grid(n4), EW_NT, 0, (cudaStream_t)stream>>>((const bf16*)dcat, (bf16*)g_r, (bf16*)g_1,
                                                                                   *bn_r, *bn_1, B, h, w, Cr, C1);
@@ -469,7 +481,7 @@ extern "C" int b200sp_reorg_cat_bwd(const void* dcat, void* g_r, void* g_1, cons
 }
 
 extern "C" int b200sp_head_bias(const float* bias, float* logits, int B, int N, void* stream) {
-    head_bias_kernel<<<ceil_div(B * N, 256), 256, 0, (cudaStream_t)stream>>>(bias, logits, B, N);
+    b200sp_launch_pdl(head_bias_kernel, dim3(ceil_div(B * N, 256)), dim3(256), 0, (cudaStream_t)stream, bias, logits, B, N);
     B200SP_COUNT_LAUNCH();
     B200SP_RETURN_LAST();
 }
@@ -487,7 +499,7 @@ extern "C" int b200sp_head_fwd(const b200sp_vtensor* x, const float* w, float* l
             if (e != cudaSuccess) return (int)e;
             attr_set = true;
         }
-        head_fwd2_kernel<float><<<ceil_div(HWC, HF_KC), EW_NT, smem, (cudaStream_t)stream>>>(*x, w, logits, B, HWC, C, N);
+        b200sp_launch_pdl(head_fwd2_kernel<float>, dim3(ceil_div(HWC, HF_KC)), dim3(EW_NT), smem, (cudaStream_t)stream, *x, w, logits, B, HWC, C, N);
         B200SP_COUNT_LAUNCH();
         B200SP_RETURN_LAST();
     }
@@ -500,7 +512,7 @@ extern "C" int b200sp_head_fwd(const b200sp_vtensor* x, const float* w, float* l
 extern "C" int b200sp_krn_loss(const float* logits, const float* target, float* loss3, float* dlogits,
                                float* dbias, const float* loss_scale, int B, int N, void* stream) {
     if (N > EW_NT || N % 2) return B200SP_EINVAL;
-    krn_loss_kernel<<<1, EW_NT, 0, (cudaStream_t)stream>>>(logits, target, loss3, dlogits, dbias, loss_scale, B, N);
+    b200sp_launch_pdl(krn_loss_kernel, dim3(1), dim3(EW_NT), 0, (cudaStream_t)stream, logits, target, loss3, dlogits, dbias, loss_scale, B, N);
     B200SP_COUNT_LAUNCH();
     B200SP_RETURN_LAST();
 }
@@ -514,8 +526,8 @@ extern "C" int b200sp_head_bwd(const float* dlogits, const b200sp_vtensor* x, co
     const size_t smem = (size_t)B * HEAD_MAXN * sizeof(float);
     if (smem > 48 * 1024) return B200SP_EINVAL;
     if (dtype == B200SP_F32)
-        head_bwd_kernel<float><<<ceil_div(HWC, EW_NT), EW_NT, smem, (cudaStream_t)stream>>>(dlogits, *x, w, (float*)g, dw, dbias, b, bn != nullptr,
-                                                                                            B, HWC, C, N);
+        b200sp_launch_pdl(head_bwd_kernel<float>, dim3(ceil_div(HWC, EW_NT)), dim3(EW_NT), smem, (cudaStream_t)stream, dlogits, *x, w, (float*)g, dw, dbias, b,
+                          (int)(bn != nullptr), B, HWC, C, N);
     else
         head_bwd_kernel<bf16><<<ceil_div(HWC, EW_NT), EW_NT, smem, (cudaStream_t)stream>>>(dlogits, *x, w, (bf16*)g, dw, dbias, b, bn != nullptr,
                                                                                            B, HWC, C, N);
