@@ -113,7 +113,8 @@ int64_t b200sp_launch_count(void);
  * converter-free TMA -> tcgen05 kernel on them.  `base`: device memory, 256-byte aligned, owned by the caller and alive until
  * replaced (NULL withdraws it); 96 MB covers every layer of the KRN.  Without a workspace the general kernel is used.  The
  * first half is reused by every eligible forward / data-gradient call, the second half by every eligible weight-gradient
- * call: issue each kind on ONE stream at a time (the engines run the weight gradients on a side stream). */
+ * call: issue each kind on ONE stream at a time (the engines run the weight gradients on a side stream).  The pointer is
+ * process-global: one device per process (the launch model of this library: one process per GPU). */
 int b200sp_set_workspace(void *base, size_t bytes);
 
 /* tcgen05 plumbing self-test (tc_probe.cu): D[128,N] = A * B^T on one CTA with operands staged in the
